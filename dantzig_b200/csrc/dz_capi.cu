@@ -1,0 +1,527 @@
+// dz_capi.cu -- the extern "C" boundary declared in include/dantzig_b200.h.
+//
+// Host runtime around the kernels: template upload, device-resident batches
+// (inputs stay in HBM between solves), streams, CUDA-event timing, result
+// download.  No CPU solve path exists here: without a usable CUDA device every
+// solve entry point returns DZ_ERR_CUDA.
+
+#include "dz_internal.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+namespace dz {
+static thread_local std::string g_err;
+void set_error(const std::string &s) { g_err = s; }
+} // namespace dz
+
+using dz::g_err;
+
+#define DZ_CUDA(call)                                                                             \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e__);                         \
+            return DZ_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+struct dz_template {
+    dz::Template host;
+    // device copies, one per device ordinal, created lazily
+    struct Dev {
+        int device = -1;
+        int32_t *blob = nullptr;
+        dz::TemplateDev view{};
+    };
+    std::vector<Dev> devs;
+    std::mutex mu;
+};
+
+static int template_on_device(dz_template *t, int device, dz::TemplateDev *view) {
+    std::lock_guard<std::mutex> lock(t->mu);
+    for (auto &d : t->devs)
+        if (d.device == device) {
+            *view = d.view;
+            return DZ_OK;
+        }
+    const dz::Template &h = t->host;
+    const size_t nnz = h.row_idx.size();
+    const size_t n_orig = h.orig_var.size();
+    const size_t total = (size_t)h.n_int + 1 + 2 * nnz + (size_t)h.n_int + 2 * (size_t)h.m +
+                         (size_t)(h.n_int - h.m) + 2 * n_orig;
+    std::vector<int32_t> blob;
+    blob.reserve(total);
+    auto push = [&](const std::vector<int32_t> &v) {
+        size_t at = blob.size();
+        blob.insert(blob.end(), v.begin(), v.end());
+        return at;
+    };
+    std::vector<int32_t> cp32(h.col_ptr.begin(), h.col_ptr.end());
+    const size_t o_cp = push(cp32), o_ri = push(h.row_idx), o_vr = push(h.val_ref);
+    const size_t o_c = push(h.c_ref), o_b = push(h.b_ref), o_b0 = push(h.basis0);
+    const size_t o_n0 = push(h.nonbasis0), o_pi = push(h.pos_index), o_ni = push(h.neg_index);
+    DZ_CUDA(cudaSetDevice(device));
+    dz_template::Dev d;
+    d.device = device;
+    DZ_CUDA(cudaMalloc(&d.blob, sizeof(int32_t) * std::max<size_t>(blob.size(), 1)));
+    DZ_CUDA(cudaMemcpy(d.blob, blob.data(), sizeof(int32_t) * blob.size(),
+                       cudaMemcpyHostToDevice));
+    d.view.M = h.m;
+    d.view.Nint = h.n_int;
+    d.view.Nn = h.n_int - h.m;
+    d.view.n_orig = (int32_t)n_orig;
+    d.view.c0_ref = h.c0_ref;
+    d.view.col_ptr = d.blob + o_cp;
+    d.view.row_idx = d.blob + o_ri;
+    d.view.val_ref = d.blob + o_vr;
+    d.view.c_ref = d.blob + o_c;
+    d.view.b_ref = d.blob + o_b;
+    d.view.basis0 = d.blob + o_b0;
+    d.view.nonbasis0 = d.blob + o_n0;
+    d.view.pos_index = d.blob + o_pi;
+    d.view.neg_index = d.blob + o_ni;
+    t->devs.push_back(d);
+    *view = d.view;
+    return DZ_OK;
+}
+
+struct dz_batch {
+    dz_template *tmpl = nullptr;
+    int64_t B = 0;
+    dz_options opt{};
+    dz::TemplateDev tview{};
+    dz::LaunchPlan plan;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    // device memory
+    double *d_theta = nullptr;
+    unsigned char *d_out = nullptr; // one slab for all outputs
+    size_t out_bytes = 0;
+    dz::BatchDev bd{};
+    double *d_gws = nullptr;
+    unsigned int *d_counter = nullptr;
+    // pinned staging for the download
+    unsigned char *h_out = nullptr;
+    size_t off_status = 0, off_pivots = 0, off_nprimal = 0, off_hash = 0, off_obj = 0,
+           off_values = 0, off_x = 0, off_basis = 0, off_trace = 0, off_work = 0;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+void dz_options_default(dz_options *o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+}
+
+int dz_template_create(const dz_model *structure, dz_template **out) {
+    if (!out) {
+        g_err = "dz_template_create: out is NULL";
+        return DZ_ERR_ARG;
+    }
+    *out = nullptr;
+    auto *t = new (std::nothrow) dz_template();
+    if (!t) {
+        g_err = "out of host memory";
+        return DZ_ERR_ALLOC;
+    }
+    int rc = dz::build_template(structure, &t->host, &g_err);
+    if (rc != DZ_OK) {
+        delete t;
+        return rc;
+    }
+    *out = t;
+    return DZ_OK;
+}
+
+void dz_template_destroy(dz_template *t) {
+    if (!t) return;
+    for (auto &d : t->devs) {
+        if (cudaSetDevice(d.device) == cudaSuccess) cudaFree(d.blob);
+    }
+    delete t;
+}
+
+int dz_template_get_info(const dz_template *t, dz_template_info *info) {
+    if (!t || !info) {
+        g_err = "dz_template_get_info: NULL argument";
+        return DZ_ERR_ARG;
+    }
+    info->m = t->host.m;
+    info->n_int = t->host.n_int;
+    info->n_orig = (int32_t)t->host.orig_var.size();
+    info->nnz = (int64_t)t->host.row_idx.size();
+    info->n_theta = t->host.n_theta;
+    return DZ_OK;
+}
+
+int dz_template_get_arrays(const dz_template *t, int64_t *col_ptr, int32_t *row_idx,
+                           int32_t *val_ref, int32_t *c_ref, int32_t *b_ref, int32_t *basis0,
+                           int32_t *nonbasis0, int32_t *orig_var, int32_t *pos_index,
+                           int32_t *neg_index) {
+    if (!t) {
+        g_err = "dz_template_get_arrays: NULL template";
+        return DZ_ERR_ARG;
+    }
+    auto cp = [](auto *dst, const auto &src) {
+        if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(src[0]));
+    };
+    const dz::Template &h = t->host;
+    cp(col_ptr, h.col_ptr);
+    cp(row_idx, h.row_idx);
+    cp(val_ref, h.val_ref);
+    cp(c_ref, h.c_ref);
+    cp(b_ref, h.b_ref);
+    cp(basis0, h.basis0);
+    cp(nonbasis0, h.nonbasis0);
+    cp(orig_var, h.orig_var);
+    cp(pos_index, h.pos_index);
+    cp(neg_index, h.neg_index);
+    return DZ_OK;
+}
+
+int dz_template_pack_theta(const dz_template *t, const dz_model *model, double *theta) {
+    if (!t || !model || !theta) {
+        g_err = "dz_template_pack_theta: NULL argument";
+        return DZ_ERR_ARG;
+    }
+    return dz::pack_theta(&t->host, model, theta, &g_err);
+}
+
+int dz_batch_create(const dz_template *tc, int64_t B, const dz_options *opt, dz_batch **out) {
+    if (!tc || !out || B <= 0 || B >= (int64_t(1) << 31)) {
+        g_err = "dz_batch_create: bad argument (need template, out, 0 < B < 2^31)";
+        return DZ_ERR_ARG;
+    }
+    *out = nullptr;
+    dz_template *t = const_cast<dz_template *>(tc);
+    auto *b = new (std::nothrow) dz_batch();
+    if (!b) {
+        g_err = "out of host memory";
+        return DZ_ERR_ALLOC;
+    }
+    b->tmpl = t;
+    b->B = B;
+    if (opt)
+        b->opt = *opt;
+    else
+        dz_options_default(&b->opt);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        g_err = std::string("no CUDA device available (the solver has no CPU path): ") +
+                cudaGetErrorString(ce);
+        delete b;
+        return DZ_ERR_CUDA;
+    }
+    if (b->opt.device < 0 || b->opt.device >= ndev) {
+        g_err = "dz_batch_create: device ordinal out of range";
+        delete b;
+        return DZ_ERR_ARG;
+    }
+    int rc = DZ_OK;
+    auto fail = [&](int code) {
+        dz_batch_destroy(b);
+        return code;
+    };
+    if (cudaSetDevice(b->opt.device) != cudaSuccess) {
+        g_err = "cudaSetDevice failed";
+        return fail(DZ_ERR_CUDA);
+    }
+    rc = template_on_device(t, b->opt.device, &b->tview);
+    if (rc != DZ_OK) return fail(rc);
+    const dz::Template &h = t->host;
+    rc = dz::plan_launch(b->opt.device, h.m, h.n_int - h.m, B, b->opt.threads_per_row,
+                         b->opt.ctas_per_sm, &b->plan, &g_err);
+    if (rc != DZ_OK) return fail(rc);
+    if (b->opt.stream) {
+        b->stream = (cudaStream_t)b->opt.stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            g_err = "cudaStreamCreate failed";
+            return fail(DZ_ERR_CUDA);
+        }
+        b->own_stream = true;
+    }
+    cudaEventCreate(&b->ev0);
+    cudaEventCreate(&b->ev1);
+
+    const size_t M = (size_t)h.m, n_orig = h.orig_var.size();
+    const size_t tc3 = (size_t)std::max(0, b->opt.trace_cap) * 3;
+    size_t off = 0;
+    auto place = [&](size_t bytes) {
+        size_t at = off;
+        off = align_up(off + bytes, 256);
+        return at;
+    };
+    b->off_status = place(sizeof(int32_t) * (size_t)B);
+    b->off_pivots = place(sizeof(int32_t) * (size_t)B);
+    b->off_nprimal = place(sizeof(int32_t) * (size_t)B);
+    b->off_hash = place(sizeof(uint64_t) * (size_t)B);
+    b->off_obj = place(sizeof(double) * (size_t)B);
+    b->off_values = place(sizeof(double) * (size_t)B * n_orig);
+    b->off_x = place(sizeof(double) * (size_t)B * M);
+    b->off_basis = place(sizeof(int32_t) * (size_t)B * M);
+    b->off_work = place(sizeof(double) * (size_t)B * 4);
+    b->off_trace = place(sizeof(int32_t) * (size_t)B * tc3);
+    b->out_bytes = off;
+    const size_t theta_bytes = sizeof(double) * (size_t)B * (size_t)h.n_theta;
+    if (cudaMalloc(&b->d_theta, std::max<size_t>(theta_bytes, 8)) != cudaSuccess ||
+        cudaMalloc(&b->d_out, std::max<size_t>(b->out_bytes, 8)) != cudaSuccess ||
+        cudaMalloc(&b->d_counter, sizeof(unsigned int)) != cudaSuccess) {
+        g_err = "cudaMalloc failed for the batch buffers";
+        cudaGetLastError();
+        return fail(DZ_ERR_ALLOC);
+    }
+    if (b->plan.gws_doubles_per_cta > 0) {
+        const size_t bytes = sizeof(double) * (size_t)b->plan.gws_doubles_per_cta * b->plan.grid;
+        if (cudaMalloc(&b->d_gws, bytes) != cudaSuccess) {
+            g_err = "cudaMalloc failed for the basis workspace";
+            cudaGetLastError();
+            return fail(DZ_ERR_ALLOC);
+        }
+    }
+    dz::BatchDev &bd = b->bd;
+    bd.B = B;
+    bd.theta = b->d_theta;
+    bd.n_theta = h.n_theta;
+    bd.max_pivots = b->opt.max_pivots > 0 ? b->opt.max_pivots
+                                          : 100 * ((int64_t)h.m + (int64_t)h.n_int) + 1000;
+    bd.trace_cap = std::max(0, b->opt.trace_cap);
+    bd.status = reinterpret_cast<int32_t *>(b->d_out + b->off_status);
+    bd.pivots = reinterpret_cast<int32_t *>(b->d_out + b->off_pivots);
+    bd.n_primal = reinterpret_cast<int32_t *>(b->d_out + b->off_nprimal);
+    bd.trace_hash = reinterpret_cast<unsigned long long *>(b->d_out + b->off_hash);
+    bd.objective = reinterpret_cast<double *>(b->d_out + b->off_obj);
+    bd.values = reinterpret_cast<double *>(b->d_out + b->off_values);
+    bd.x_basic = reinterpret_cast<double *>(b->d_out + b->off_x);
+    bd.basis = reinterpret_cast<int32_t *>(b->d_out + b->off_basis);
+    bd.work = reinterpret_cast<double *>(b->d_out + b->off_work);
+    bd.trace = tc3 ? reinterpret_cast<int32_t *>(b->d_out + b->off_trace) : nullptr;
+    bd.next_lp = b->d_counter;
+    bd.gws = b->d_gws;
+    bd.gws_stride = b->plan.gws_doubles_per_cta;
+    *out = b;
+    return DZ_OK;
+}
+
+void dz_batch_destroy(dz_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->opt.device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_theta);
+    cudaFree(b->d_out);
+    cudaFree(b->d_counter);
+    cudaFree(b->d_gws);
+    if (b->h_out) cudaFreeHost(b->h_out);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+    cudaGetLastError();
+    delete b;
+}
+
+int dz_batch_upload(dz_batch *b, const double *theta) {
+    if (!b || !theta) {
+        g_err = "dz_batch_upload: NULL argument";
+        return DZ_ERR_ARG;
+    }
+    DZ_CUDA(cudaSetDevice(b->opt.device));
+    const size_t bytes = sizeof(double) * (size_t)b->B * (size_t)b->tmpl->host.n_theta;
+    DZ_CUDA(cudaMemcpyAsync(b->d_theta, theta, bytes, cudaMemcpyHostToDevice, b->stream));
+    return DZ_OK;
+}
+
+int dz_batch_solve(dz_batch *b) {
+    if (!b) {
+        g_err = "dz_batch_solve: NULL batch";
+        return DZ_ERR_ARG;
+    }
+    DZ_CUDA(cudaSetDevice(b->opt.device));
+    DZ_CUDA(cudaMemsetAsync(b->d_counter, 0, sizeof(unsigned int), b->stream));
+    DZ_CUDA(cudaMemsetAsync(b->d_out + b->off_work, 0, sizeof(double) * (size_t)b->B * 4,
+                            b->stream));
+    DZ_CUDA(cudaEventRecord(b->ev0, b->stream));
+    int rc = dz::launch_batch(b->tview, b->bd, b->plan, b->stream, &g_err);
+    if (rc != DZ_OK) return rc;
+    DZ_CUDA(cudaEventRecord(b->ev1, b->stream));
+    b->timed = true;
+    return DZ_OK;
+}
+
+int dz_batch_sync(dz_batch *b) {
+    if (!b) {
+        g_err = "dz_batch_sync: NULL batch";
+        return DZ_ERR_ARG;
+    }
+    DZ_CUDA(cudaSetDevice(b->opt.device));
+    DZ_CUDA(cudaStreamSynchronize(b->stream));
+    return DZ_OK;
+}
+
+int dz_batch_download(dz_batch *b, dz_batch_result *out) {
+    if (!b || !out) {
+        g_err = "dz_batch_download: NULL argument";
+        return DZ_ERR_ARG;
+    }
+    DZ_CUDA(cudaSetDevice(b->opt.device));
+    const size_t B = (size_t)b->B, M = (size_t)b->tmpl->host.m;
+    const size_t n_orig = b->tmpl->host.orig_var.size();
+    const size_t tc3 = (size_t)b->bd.trace_cap * 3;
+    auto get = [&](void *dst, size_t off, size_t bytes) -> cudaError_t {
+        if (!dst || bytes == 0) return cudaSuccess;
+        return cudaMemcpyAsync(dst, b->d_out + off, bytes, cudaMemcpyDeviceToHost, b->stream);
+    };
+    DZ_CUDA(get(out->status, b->off_status, sizeof(int32_t) * B));
+    DZ_CUDA(get(out->pivots, b->off_pivots, sizeof(int32_t) * B));
+    DZ_CUDA(get(out->n_primal, b->off_nprimal, sizeof(int32_t) * B));
+    DZ_CUDA(get(out->trace_hash, b->off_hash, sizeof(uint64_t) * B));
+    DZ_CUDA(get(out->objective, b->off_obj, sizeof(double) * B));
+    DZ_CUDA(get(out->values, b->off_values, sizeof(double) * B * n_orig));
+    DZ_CUDA(get(out->x_basic, b->off_x, sizeof(double) * B * M));
+    DZ_CUDA(get(out->basis, b->off_basis, sizeof(int32_t) * B * M));
+    DZ_CUDA(get(out->work, b->off_work, sizeof(double) * B * 4));
+    if (tc3) DZ_CUDA(get(out->trace, b->off_trace, sizeof(int32_t) * B * tc3));
+    DZ_CUDA(cudaStreamSynchronize(b->stream));
+    return DZ_OK;
+}
+
+int dz_batch_last_timing(dz_batch *b, float *kernel_ms, int32_t *launches) {
+    if (!b || !b->timed) {
+        g_err = "dz_batch_last_timing: no solve has been enqueued";
+        return DZ_ERR_ARG;
+    }
+    DZ_CUDA(cudaSetDevice(b->opt.device));
+    DZ_CUDA(cudaEventSynchronize(b->ev1));
+    float ms = 0.f;
+    DZ_CUDA(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+    if (kernel_ms) *kernel_ms = ms;
+    if (launches) *launches = 1;
+    return DZ_OK;
+}
+
+int dz_batch_launch_info(dz_batch *b, int32_t *grid, int32_t *block, int32_t *smem_bytes,
+                         int32_t *ctas_per_sm, int32_t *w_in_smem) {
+    if (!b) {
+        g_err = "dz_batch_launch_info: NULL batch";
+        return DZ_ERR_ARG;
+    }
+    if (grid) *grid = b->plan.grid;
+    if (block) *block = b->plan.block;
+    if (smem_bytes) *smem_bytes = b->plan.smem_bytes;
+    if (ctas_per_sm) *ctas_per_sm = b->plan.ctas_per_sm;
+    if (w_in_smem) *w_in_smem = b->plan.w_in_smem ? 1 : 0;
+    return DZ_OK;
+}
+
+int dz_batch_io_bytes(dz_batch *b, int64_t *h2d, int64_t *d2h) {
+    if (!b) {
+        g_err = "dz_batch_io_bytes: NULL batch";
+        return DZ_ERR_ARG;
+    }
+    if (h2d) *h2d = (int64_t)sizeof(double) * b->B * b->tmpl->host.n_theta;
+    if (d2h) *d2h = (int64_t)b->out_bytes;
+    return DZ_OK;
+}
+
+int dz_solve_batch(const dz_template *t, int64_t B, const double *theta, const dz_options *opt,
+                   dz_batch_result *out) {
+    if (!t || !theta || !out) {
+        g_err = "dz_solve_batch: NULL argument";
+        return DZ_ERR_ARG;
+    }
+    dz_batch *b = nullptr;
+    int rc = dz_batch_create(t, B, opt, &b);
+    if (rc != DZ_OK) return rc;
+    rc = dz_batch_upload(b, theta);
+    if (rc == DZ_OK) rc = dz_batch_solve(b);
+    if (rc == DZ_OK) rc = dz_batch_download(b, out);
+    dz_batch_destroy(b);
+    return rc;
+}
+
+int dz_solve_model(const dz_model *model, const dz_options *opt, dz_solution *sol,
+                   double *values) {
+    if (!model || !sol) {
+        g_err = "dz_solve_model: NULL argument";
+        return DZ_ERR_ARG;
+    }
+    dz_template *t = nullptr;
+    int rc = dz_template_create(model, &t);
+    if (rc != DZ_OK) return rc;
+    std::vector<double> theta((size_t)t->host.n_theta);
+    rc = dz::pack_theta(&t->host, model, theta.data(), &g_err);
+    if (rc != DZ_OK) {
+        dz_template_destroy(t);
+        return rc;
+    }
+    const size_t n_orig = t->host.orig_var.size();
+    std::vector<double> vals(std::max<size_t>(n_orig, 1));
+    int32_t status = 0, pivots = 0, n_primal = 0;
+    uint64_t hash = 0;
+    double objective = 0.0;
+    dz_batch_result r;
+    std::memset(&r, 0, sizeof(r));
+    r.status = &status;
+    r.pivots = &pivots;
+    r.n_primal = &n_primal;
+    r.trace_hash = &hash;
+    r.objective = &objective;
+    r.values = vals.data();
+    rc = dz_solve_batch(t, 1, theta.data(), opt, &r);
+    if (rc == DZ_OK) {
+        sol->status = status;
+        sol->pivots = pivots;
+        sol->n_primal = n_primal;
+        sol->trace_hash = hash;
+        sol->objective = objective;
+        if (values) {
+            for (int32_t v = 0; v < model->n_vars; ++v) values[v] = 0.0;
+            for (size_t k = 0; k < n_orig; ++k) values[t->host.orig_var[k]] = vals[k];
+        }
+    }
+    dz_template_destroy(t);
+    return rc;
+}
+
+const char *dz_last_error(void) { return g_err.c_str(); }
+
+int dz_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int dz_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major,
+                   int *cc_minor, int64_t *smem_per_sm) {
+    cudaDeviceProp prop;
+    DZ_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (name && name_len > 0) {
+        std::strncpy(name, prop.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (smem_per_sm) *smem_per_sm = (int64_t)prop.sharedMemPerMultiprocessor;
+    return DZ_OK;
+}
+
+int dz_version(void) { return DZ_VERSION; }
+
+int dz_measure_fp64_peak(int device, double *mul_sub_gflops, double *fma_gflops) {
+    return dz::measure_fp64_peak(device, mul_sub_gflops, fma_gflops, &g_err);
+}
+
+} // extern "C"

@@ -1,0 +1,85 @@
+// dz_internal.h -- shared host/device declarations of the dantzig_b200 library.
+#ifndef DZ_INTERNAL_H
+#define DZ_INTERNAL_H
+
+#include "../../include/dantzig_b200.h"
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace dz {
+
+// Host-side lowered template (see dz_lower.cpp).
+struct Template {
+    int32_t m = 0, n_int = 0;
+    std::vector<int64_t> col_ptr;
+    std::vector<int32_t> row_idx, val_ref;
+    std::vector<int32_t> c_ref, b_ref, basis0, nonbasis0;
+    std::vector<int32_t> orig_var, pos_index, neg_index;
+    int32_t c0_ref = -1;
+    // theta layout
+    int32_t n_vars = 0, n_obj = 0, n_rows_user = 0;
+    int64_t n_row_terms = 0;
+    int64_t off_obj = 0, off_rowcoef = 0, off_rhs = 0, off_lb = 0, off_ub = 0, n_theta = 0;
+};
+
+int build_template(const dz_model *m, Template *t, std::string *err);
+int pack_theta(const Template *t, const dz_model *m, double *theta, std::string *err);
+
+// Device view of a template: plain pointers into one device allocation.
+struct TemplateDev {
+    int32_t M, Nint, Nn, n_orig;
+    int32_t c0_ref;
+    const int32_t *col_ptr;   // [Nint+1]
+    const int32_t *row_idx;   // [nnz]
+    const int32_t *val_ref;   // [nnz]
+    const int32_t *c_ref;     // [Nint]
+    const int32_t *b_ref;     // [M]
+    const int32_t *basis0;    // [M]
+    const int32_t *nonbasis0; // [Nn]
+    const int32_t *pos_index; // [n_orig]
+    const int32_t *neg_index; // [n_orig]
+};
+
+// Device view of one batch: inputs and outputs, all in HBM.
+struct BatchDev {
+    int64_t B;
+    const double *theta; // [B][n_theta]
+    int64_t n_theta;
+    int64_t max_pivots;
+    int32_t trace_cap;
+    int32_t *status;
+    int32_t *pivots;
+    int32_t *n_primal;
+    unsigned long long *trace_hash;
+    double *objective;
+    double *values;  // [B][n_orig]
+    double *x_basic; // [B][M]
+    int32_t *basis;  // [B][M]
+    int32_t *trace;  // [B][trace_cap][3] or null
+    double *work;    // [B][4]
+    unsigned int *next_lp; // work-queue counter
+    double *gws;     // global workspace for the basis when it does not fit in smem
+    int64_t gws_stride; // doubles per CTA
+};
+
+// Launch plan computed on the host (dz_kernel.cu).
+struct LaunchPlan {
+    int32_t grid = 0, block = 0, smem_bytes = 0, ctas_per_sm = 0, tpr = 1;
+    bool w_in_smem = true;
+    int64_t gws_doubles_per_cta = 0;
+};
+
+int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t tpr_hint, int32_t cps_hint,
+                LaunchPlan *plan, std::string *err);
+// Enqueue the batched solve on `stream` (cudaStream_t passed as void*).
+int launch_batch(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan, void *stream,
+                 std::string *err);
+int measure_fp64_peak(int device, double *mul_sub_gflops, double *fma_gflops, std::string *err);
+
+void set_error(const std::string &s);
+
+} // namespace dz
+
+#endif

@@ -1,0 +1,825 @@
+// dz_kernel.cu -- batched CTA-per-LP parametric self-dual simplex for sm_100a.
+//
+// One persistent CTA solves one LP at a time (work queue over the batch); the
+// whole pivot loop of Simplex::solve (/root/reference/src/simplex.rs:274-343)
+// runs on the device with no host round trip.  Per pivot the CTA
+//   * gathers the basis from the CSC template into a dense working matrix W
+//     held in shared memory (replaces basis_matrix/collect_columns/to_dense/t,
+//     simplex.rs:270-272, linalg.rs:40-48,131-140,188-192),
+//   * eliminates [W | rhs] with partial pivoting in the reference's exact
+//     operation order (Matrix::factorize linalg.rs:88-128 fused with the forward
+//     half of LU::solve linalg.rs:286-291), once for B and once for B^T,
+//   * back-substitutes (linalg.rs:292-297),
+//   * prices dz = -N^T v over the CSC columns (neg_t_dot linalg.rs:199-207),
+//   * runs the ratio tests / arg-max rules with first-index tie-breaks
+//     (find_first_pivot, find_second_pivot simplex.rs:423-461) and the four
+//     vector updates (pivot simplex.rs:253-268,410-421).
+//
+// EXACTNESS CONTRACT.  Results must be bit-identical to the reference's CPU
+// arithmetic, so every floating point operation of the reference is performed
+// in binary64 with round-to-nearest, unfused (__dmul_rn/__dsub_rn/__ddiv_rn;
+// the file is also compiled with --fmad=false) and in the reference's order
+// wherever order matters.  The only liberties taken are ones that cannot
+// change a bit of any value the algorithm observes:
+//   * operations with an exact-zero factor and a finite co-factor are skipped;
+//   * elimination steps whose pivot column holds a single nonzero in a row that
+//     has not been used yet ("virgin unit" steps: every slack column is one
+//     until its row is stolen) are pure bookkeeping and are retired by one
+//     control thread without touching the matrix;
+//   * L is never stored: the right-hand side rides along as column M of W, so
+//     the forward substitution happens inside the elimination;
+//   * rows are never physically swapped: a logical-position table records the
+//     interchanges (positions decide the pivot-search tie-break).
+// When a back-substitution produces a non-finite value the skipping rules are
+// no longer no-ops (0*inf = NaN), so that solve is redone without skipping.
+//
+// THREAD MAP.  TPR*MP worker threads (MP = M rounded up to a warp): worker
+// (h, r) owns row r of W and the columns j == k+1+h (mod TPR) of the trailing
+// update, so an element is only ever written by the thread that reads it in the
+// next pivot search; plus one control warp that retires the virgin-unit steps,
+// keeps the position tables and runs the serial part of back-substitution.
+
+#include "dz_internal.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+
+namespace dz {
+
+namespace {
+
+constexpr int kMaxWarps = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ double load_ref(const double *__restrict__ th, int ref) {
+    if (ref < 0) return 0.0;
+    const double v = __ldg(th + (ref >> 1));
+    return (ref & 1) ? -v : v;
+}
+
+// Total order used by every arg-max on the path: larger key first, then the
+// smaller index ("first index wins", simplex.rs:432-435, linalg.rs:100-105).
+__device__ __forceinline__ bool beats(double k2, int i2, double k1, int i1) {
+    return i2 >= 0 && (i1 < 0 || k2 > k1 || (k2 == k1 && i2 < i1));
+}
+
+template <int N> struct Cand {
+    double key[N];
+    int idx[N];
+};
+
+// Block-wide arg-max of N independent (key, idx) candidates with one barrier.
+// red_key/red_idx hold [2][N][kMaxWarps]; `parity` alternates between calls so
+// a slot is never rewritten before every thread has read it.
+template <int N>
+__device__ __forceinline__ void block_argmax(Cand<N> &c, double *red_key, int *red_idx,
+                                             int &parity, int nwarps) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double k2 = __shfl_xor_sync(kFull, c.key[n], off);
+            const int i2 = __shfl_xor_sync(kFull, c.idx[n], off);
+            if (beats(k2, i2, c.key[n], c.idx[n])) {
+                c.key[n] = k2;
+                c.idx[n] = i2;
+            }
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *rk = red_key + (size_t)parity * N * kMaxWarps;
+    int *ri = red_idx + (size_t)parity * N * kMaxWarps;
+    if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            rk[n * kMaxWarps + warp] = c.key[n];
+            ri[n * kMaxWarps + warp] = c.idx[n];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        double bk = rk[n * kMaxWarps];
+        int bi = ri[n * kMaxWarps];
+        for (int w = 1; w < nwarps; ++w) {
+            const double k2 = rk[n * kMaxWarps + w];
+            const int i2 = ri[n * kMaxWarps + w];
+            if (beats(k2, i2, bk, bi)) {
+                bk = k2;
+                bi = i2;
+            }
+        }
+        c.key[n] = bk;
+        c.idx[n] = bi;
+    }
+    parity ^= 1;
+}
+
+struct Ctx {
+    // problem
+    int M, Nn, S, MP, NW, nthreads, nwarps;
+    // shared-memory arrays
+    double *W;
+    double *x, *xb, *dxv, *vv, *z, *zb, *dzv;
+    double *red_key;
+    int *bas, *nb, *rowAt, *posOf, *cnt, *unitRow, *retired, *pend, *red_idx, *ctl;
+    int parity;
+    // counters (per thread)
+    unsigned long long n_lu, n_solve, n_price;
+};
+
+enum { CTL_K = 0, CTL_FLAG = 1, CTL_LP = 2 };
+
+// find_first_pivot (simplex.rs:423-437) for both the dual (z) and primal (x)
+// sides with a single barrier.  Returns positions (-1 = None).  The reference's
+// sequential reduce keeps its FIRST element when that element's ratio is NaN
+// (nothing compares greater than NaN); otherwise NaN ratios never win.
+__device__ __forceinline__ void find_first_both(Ctx &c, int &q0, int &p0) {
+    Cand<4> cd;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        cd.key[n] = 0.0;
+        cd.idx[n] = -1;
+    }
+    for (int k = threadIdx.x; k < c.Nn; k += c.nthreads) {
+        const double yb = c.zb[k];
+        if (yb > 0.0) {
+            const double ratio = __ddiv_rn(-c.z[k], yb);
+            if (ratio == ratio && beats(ratio, k, cd.key[0], cd.idx[0])) {
+                cd.key[0] = ratio;
+                cd.idx[0] = k;
+            }
+            if (cd.idx[1] < 0) cd.idx[1] = k; // k ascends per thread
+        }
+    }
+    for (int k = threadIdx.x; k < c.M; k += c.nthreads) {
+        const double yb = c.xb[k];
+        if (yb > 0.0) {
+            const double ratio = __ddiv_rn(-c.x[k], yb);
+            if (ratio == ratio && beats(ratio, k, cd.key[2], cd.idx[2])) {
+                cd.key[2] = ratio;
+                cd.idx[2] = k;
+            }
+            if (cd.idx[3] < 0) cd.idx[3] = k;
+        }
+    }
+    block_argmax<4>(cd, c.red_key, c.red_idx, c.parity, c.nwarps);
+    q0 = cd.idx[0];
+    if (cd.idx[1] >= 0) {
+        const double r = __ddiv_rn(-c.z[cd.idx[1]], c.zb[cd.idx[1]]);
+        if (r != r) q0 = cd.idx[1];
+    }
+    p0 = cd.idx[2];
+    if (cd.idx[3] >= 0) {
+        const double r = __ddiv_rn(-c.x[cd.idx[3]], c.xb[cd.idx[3]]);
+        if (r != r) p0 = cd.idx[3];
+    }
+}
+
+// find_second_pivot (simplex.rs:439-461): arg-max of dy/(y + mu*ybar) over the
+// strictly positive ratios, first index wins.  Returns the position or -1.
+__device__ __forceinline__ int find_second(Ctx &c, double mu, const double *y, const double *yb,
+                                           const double *dy, int len) {
+    Cand<1> cd;
+    cd.key[0] = 0.0;
+    cd.idx[0] = -1;
+    for (int k = threadIdx.x; k < len; k += c.nthreads) {
+        const double denom = __dadd_rn(y[k], __dmul_rn(mu, yb[k]));
+        const double ratio = __ddiv_rn(dy[k], denom);
+        if (ratio > 0.0 && beats(ratio, k, cd.key[0], cd.idx[0])) {
+            cd.key[0] = ratio;
+            cd.idx[0] = k;
+        }
+    }
+    block_argmax<1>(cd, c.red_key, c.red_idx, c.parity, c.nwarps);
+    return cd.idx[0];
+}
+
+// Back substitution (linalg.rs:292-297) over the eliminated [W | rhs].
+// literal == false: rows whose strict upper part is all zero are solved by
+// their own threads up front; the others run serially on the control warp with
+// exact-zero products skipped.  literal == true: every term, strictly serial.
+// Sets ctl[CTL_FLAG] when a non-finite value is produced.
+template <int TPR>
+__device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal) {
+    const int M = c.M, S = c.S, tid = threadIdx.x;
+    const bool worker = tid < c.NW;
+    const int r = tid % c.MP, h = tid / c.MP;
+    double *W = c.W;
+    if (worker && h == 0 && r < M) {
+        const int i = c.posOf[r];
+        bool has_nz = literal;
+        if (!literal) {
+            const double *row = W + (size_t)r * S;
+            for (int j = i + 1; j < M; ++j)
+                if (row[j] != 0.0) {
+                    has_nz = true;
+                    break;
+                }
+        }
+        c.pend[i] = has_nz ? 1 : 0;
+        if (!has_nz) {
+            const double yi = __ddiv_rn(W[(size_t)r * S + M], W[(size_t)r * S + i]);
+            y[i] = yi;
+            if (!isfinite(yi)) c.ctl[CTL_FLAG] = 1;
+            c.n_solve += 1;
+        }
+    }
+    __syncthreads();
+    if (!worker) { // control warp
+        const int lane = tid - c.NW;
+        for (int base = (M - 1) & ~31; base >= 0; base -= 32) {
+            const int il = base + lane;
+            unsigned pm = __ballot_sync(kFull, il < M && c.pend[il] != 0);
+            while (pm) {
+                const int bit = 31 - __clz(pm);
+                pm &= ~(1u << bit);
+                const int i = base + bit;
+                const double *row = W + (size_t)c.rowAt[i] * S;
+                double s = row[M];
+                for (int j0 = i + 1; j0 < M; j0 += 32) {
+                    const int j = j0 + lane;
+                    double u = 0.0, yj = 0.0;
+                    if (j < M) {
+                        u = row[j];
+                        yj = y[j];
+                    }
+                    const double t = __dmul_rn(u, yj);
+                    unsigned mk = __ballot_sync(kFull, literal ? (j < M) : (u != 0.0 && yj != 0.0));
+                    if (lane == 0) c.n_solve += 2ull * __popc(mk);
+                    while (mk) {
+                        const int b = __ffs(mk) - 1;
+                        mk &= mk - 1;
+                        s = __dsub_rn(s, __shfl_sync(kFull, t, b));
+                    }
+                }
+                const double yi = __ddiv_rn(s, row[i]);
+                if (lane == 0) {
+                    y[i] = yi;
+                    if (!isfinite(yi)) c.ctl[CTL_FLAG] = 1;
+                    c.n_solve += 1;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// lu_solve (linalg.rs:8-10) of B (transposed == false, rhs = column `arg` of A)
+// or of B^T (transposed == true, rhs = e_arg).  Result in y[0..M).
+template <int TPR>
+__device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
+                                            const double *__restrict__ theta, bool transposed,
+                                            int arg, double *y) {
+    const int M = c.M, S = c.S, tid = threadIdx.x;
+    double *W = c.W;
+    const bool worker = tid < c.NW;
+    const int r = tid % c.MP, h = tid / c.MP;
+
+    // ---- gather: W = dense(B) or dense(B^T), rhs in column M ----------------
+    {
+        const int total = M * S;
+        for (int e = tid; e < total; e += c.nthreads) W[e] = 0.0;
+        for (int i = tid; i < M; i += c.nthreads) {
+            c.cnt[i] = 0;
+            c.unitRow[i] = -1;
+            c.rowAt[i] = i;
+            c.posOf[i] = i;
+            c.retired[i] = 0;
+        }
+        if (tid == 0) c.ctl[CTL_FLAG] = 0;
+    }
+    __syncthreads();
+    for (int p = tid; p < M; p += c.nthreads) {
+        const int col = c.bas[p];
+        const int e0 = T.col_ptr[col], e1 = T.col_ptr[col + 1];
+        int mycnt = 0, myrow = -1;
+        for (int e = e0; e < e1; ++e) {
+            const double v = load_ref(theta, T.val_ref[e]);
+            if (v != 0.0) {
+                const int row = T.row_idx[e];
+                if (!transposed) {
+                    W[(size_t)row * S + p] = v;
+                    ++mycnt;
+                    myrow = row;
+                } else {
+                    W[(size_t)p * S + row] = v;
+                    atomicAdd(&c.cnt[row], 1);
+                    c.unitRow[row] = p; // meaningful only where cnt ends at 1
+                }
+            }
+        }
+        if (!transposed) {
+            c.cnt[p] = mycnt;
+            c.unitRow[p] = myrow;
+        }
+    }
+    if (!transposed) {
+        const int e0 = T.col_ptr[arg], e1 = T.col_ptr[arg + 1];
+        for (int e = e0 + tid; e < e1; e += c.nthreads) {
+            const double v = load_ref(theta, T.val_ref[e]);
+            if (v != 0.0) W[(size_t)T.row_idx[e] * S + M] = v;
+        }
+    } else if (tid == 0) {
+        W[(size_t)arg * S + M] = 1.0;
+    }
+    __syncthreads();
+
+    // ---- elimination ---------------------------------------------------------
+    int k = 0;
+    for (;;) {
+        if (tid == c.NW) { // control thread: retire virgin-unit / empty columns
+            while (k < M - 1) {
+                const int cn = c.cnt[k];
+                if (cn == 0) { // all-zero column: mu = k, pivot 0, nothing moves (linalg.rs:117)
+                    c.retired[c.rowAt[k]] = 1;
+                    ++k;
+                    continue;
+                }
+                if (cn == 1) {
+                    const int ur = c.unitRow[k];
+                    if (!c.retired[ur]) {
+                        const int mu = c.posOf[ur], rk = c.rowAt[k];
+                        c.rowAt[k] = ur;
+                        c.rowAt[mu] = rk;
+                        c.posOf[ur] = k;
+                        c.posOf[rk] = mu;
+                        c.retired[ur] = 1;
+                        ++k;
+                        continue;
+                    }
+                }
+                break;
+            }
+            c.ctl[CTL_K] = k;
+        }
+        __syncthreads();
+        k = c.ctl[CTL_K];
+        if (k >= M - 1) break;
+
+        // pivot search over the active rows of column k (linalg.rs:98-105)
+        Cand<1> cd;
+        cd.key[0] = 0.0;
+        cd.idx[0] = -1;
+        double v = 0.0;
+        bool active = false;
+        if (worker && r < M) {
+            const int myPos = c.posOf[r];
+            active = myPos >= k;
+            if (active) {
+                v = W[(size_t)r * S + k];
+                if (h == 0) {
+                    double key = fabs(v);
+                    if (v != v) key = (myPos == k) ? __longlong_as_double(0x7ff0000000000000LL) : -1.0;
+                    cd.key[0] = key;
+                    cd.idx[0] = (myPos << 16) | r;
+                }
+            }
+        }
+        block_argmax<1>(cd, c.red_key, c.red_idx, c.parity, c.nwarps);
+        const int pr = cd.idx[0] & 0xffff, ppos = cd.idx[0] >> 16;
+        const double pv = W[(size_t)pr * S + k];
+        if (pv != 0.0 && active && r != pr && v != 0.0) {
+            const double l = __ddiv_rn(v, pv);
+            const double *prow = W + (size_t)pr * S;
+            double *myrow = W + (size_t)r * S;
+            unsigned nupd = 0;
+            for (int j = k + 1 + h; j <= M; j += TPR) {
+                const double u = prow[j];
+                if (u != 0.0) {
+                    myrow[j] = __dsub_rn(myrow[j], __dmul_rn(l, u));
+                    ++nupd;
+                }
+            }
+            c.n_lu += 2ull * nupd + (h == 0 ? 1 : 0);
+        }
+        if (tid == c.NW) { // record the interchange k <-> ppos
+            const int rk = c.rowAt[k];
+            c.rowAt[k] = pr;
+            c.rowAt[ppos] = rk;
+            c.posOf[pr] = k;
+            c.posOf[rk] = ppos;
+            c.retired[pr] = 1;
+        }
+        ++k;
+    }
+    // ---- back substitution ------------------------------------------------------
+    back_substitute<TPR>(c, y, false);
+    if (c.ctl[CTL_FLAG]) {
+        __syncthreads();
+        if (tid == 0) c.ctl[CTL_FLAG] = 0;
+        back_substitute<TPR>(c, y, true);
+    }
+}
+
+template <int TPR, bool WSMEM>
+__global__ void __launch_bounds__(1024, 1)
+dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Ctx c;
+    c.M = T.M;
+    c.Nn = T.Nn;
+    c.S = (T.M + 1) | 1;
+    c.MP = (T.M + 31) & ~31;
+    c.NW = TPR * c.MP;
+    c.nthreads = blockDim.x;
+    c.nwarps = blockDim.x >> 5;
+    c.parity = 0;
+    const int M = c.M, Nn = c.Nn, tid = threadIdx.x;
+    {
+        double *dp = reinterpret_cast<double *>(smem_raw);
+        if (WSMEM) {
+            c.W = dp;
+            dp += (size_t)M * c.S;
+        } else {
+            c.W = Bt.gws + (size_t)blockIdx.x * Bt.gws_stride;
+        }
+        c.x = dp, dp += M;
+        c.xb = dp, dp += M;
+        c.dxv = dp, dp += M;
+        c.vv = dp, dp += M;
+        c.z = dp, dp += Nn;
+        c.zb = dp, dp += Nn;
+        c.dzv = dp, dp += Nn;
+        c.red_key = dp, dp += 2 * 4 * kMaxWarps;
+        int *ip = reinterpret_cast<int *>(dp);
+        c.bas = ip, ip += M;
+        c.nb = ip, ip += Nn;
+        c.rowAt = ip, ip += M;
+        c.posOf = ip, ip += M;
+        c.cnt = ip, ip += M;
+        c.unitRow = ip, ip += M;
+        c.retired = ip, ip += M;
+        c.pend = ip, ip += M;
+        c.red_idx = ip, ip += 2 * 4 * kMaxWarps;
+        c.ctl = ip, ip += 8;
+    }
+    const long long max_pivots = Bt.max_pivots;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) c.ctl[CTL_LP] = (int)atomicAdd(Bt.next_lp, 1u);
+        __syncthreads();
+        const long long lp = (unsigned)c.ctl[CTL_LP];
+        if (lp >= Bt.B) break;
+        const double *__restrict__ theta = Bt.theta + (size_t)lp * Bt.n_theta;
+        c.n_lu = c.n_solve = c.n_price = 0;
+        unsigned long long n_upd = 0;
+
+        // initial state (simplex.rs:190-205)
+        for (int p = tid; p < M; p += c.nthreads) {
+            c.bas[p] = T.basis0[p];
+            c.x[p] = load_ref(theta, T.b_ref[p]);
+            c.xb[p] = 1.0;
+        }
+        for (int k = tid; k < Nn; k += c.nthreads) {
+            const int col = T.nonbasis0[k];
+            c.nb[k] = col;
+            c.z[k] = -load_ref(theta, T.c_ref[col]);
+            c.zb[k] = 1.0;
+        }
+        __syncthreads();
+
+        int status = DZ_OPTIMAL;
+        long long pivots = 0, n_primal = 0;
+        unsigned long long hash = 0xcbf29ce484222325ULL;
+        if (M == 0) status = DZ_BREAKDOWN; // 0x0 basis: the reference panics (linalg.rs:95)
+
+        while (M > 0) {
+            // ---- status(), simplex.rs:274-306 ----
+            int q0, p0;
+            find_first_both(c, q0, p0);
+            bool primal_step;
+            double mu;
+            if (q0 >= 0 && p0 >= 0) {
+                const double primal = __ddiv_rn(-c.x[p0], c.xb[p0]);
+                const double dual = __ddiv_rn(-c.z[q0], c.zb[q0]);
+                if (primal <= 1e-12 && dual <= 1e-12) break;
+                if (primal < dual) {
+                    primal_step = true;
+                    mu = dual;
+                } else {
+                    primal_step = false;
+                    mu = primal;
+                }
+            } else if (q0 >= 0) {
+                primal_step = true;
+                mu = __ddiv_rn(-c.z[q0], c.zb[q0]);
+            } else if (p0 >= 0) {
+                primal_step = false;
+                mu = __ddiv_rn(-c.x[p0], c.xb[p0]);
+            } else {
+                status = DZ_BREAKDOWN; // "unexpected code path", simplex.rs:304
+                break;
+            }
+            if (pivots >= max_pivots) {
+                status = DZ_PIVOT_CAP;
+                break;
+            }
+            int p, q;
+            if (primal_step) { // simplex.rs:308-318
+                q = q0;
+                basis_solve<TPR>(c, T, theta, false, c.nb[q], c.dxv);
+                p = find_second(c, mu, c.x, c.xb, c.dxv, M);
+                if (p < 0) {
+                    status = DZ_UNBOUNDED;
+                    break;
+                }
+                basis_solve<TPR>(c, T, theta, true, p, c.vv);
+            } else { // simplex.rs:320-330
+                p = p0;
+                basis_solve<TPR>(c, T, theta, true, p, c.vv);
+            }
+            // pricing: dz = -N^T v (simplex.rs:235, linalg.rs:199-207)
+            for (int k = tid; k < Nn; k += c.nthreads) {
+                const int col = c.nb[k];
+                const int e0 = T.col_ptr[col], e1 = T.col_ptr[col + 1];
+                double s = 0.0;
+                for (int e = e0; e < e1; ++e) {
+                    const double a = load_ref(theta, T.val_ref[e]);
+                    if (a != 0.0) {
+                        s = __dadd_rn(s, __dmul_rn(a, -c.vv[T.row_idx[e]]));
+                        c.n_price += 2;
+                    }
+                }
+                c.dzv[k] = s;
+            }
+            __syncthreads();
+            if (!primal_step) {
+                q = find_second(c, mu, c.z, c.zb, c.dzv, Nn);
+                if (q < 0) {
+                    status = DZ_INFEASIBLE;
+                    break;
+                }
+                basis_solve<TPR>(c, T, theta, false, c.nb[q], c.dxv);
+            }
+            // ---- Simplex::pivot, simplex.rs:253-268 ----
+            const int leaving = c.bas[p], entering = c.nb[q];
+            double t, s, t_bar, s_bar;
+            bool ok = true;
+            {
+                const double xp = c.x[p], dxp = c.dxv[p], zq = c.z[q], dzq = c.dzv[q];
+                const double xbp = c.xb[p], zbq = c.zb[q];
+                t = (xp == 0.0 && dxp == 0.0) ? 0.0 : __ddiv_rn(xp, dxp);
+                s = (zq == 0.0 && dzq == 0.0) ? 0.0 : __ddiv_rn(zq, dzq);
+                t_bar = (xbp == 0.0 && dxp == 0.0) ? 0.0 : __ddiv_rn(xbp, dxp);
+                s_bar = (zbq == 0.0 && dzq == 0.0) ? 0.0 : __ddiv_rn(zbq, dzq);
+                ok = isfinite(t) && isfinite(s) && isfinite(t_bar) && isfinite(s_bar);
+            }
+            if (!ok) {
+                status = DZ_BREAKDOWN; // safe_divide assert, simplex.rs:466
+                break;
+            }
+            __syncthreads(); // everyone has read x[p], z[q], ... before they change
+            for (int k = tid; k < M; k += c.nthreads) { // fn pivot, simplex.rs:410-421
+                const double d = c.dxv[k];
+                if (k == p) {
+                    c.x[k] = t;
+                    c.xb[k] = t_bar;
+                } else {
+                    c.x[k] = __dsub_rn(c.x[k], __dmul_rn(t, d));
+                    c.xb[k] = __dsub_rn(c.xb[k], __dmul_rn(t_bar, d));
+                }
+            }
+            for (int k = tid; k < Nn; k += c.nthreads) {
+                const double d = c.dzv[k];
+                if (k == q) {
+                    c.z[k] = s;
+                    c.zb[k] = s_bar;
+                } else {
+                    c.z[k] = __dsub_rn(c.z[k], __dmul_rn(s, d));
+                    c.zb[k] = __dsub_rn(c.zb[k], __dmul_rn(s_bar, d));
+                }
+            }
+            n_upd += 4ull * (M + Nn);
+            if (tid == 0) { // swap, simplex.rs:239-251
+                c.bas[p] = entering;
+                c.nb[q] = leaving;
+                if (Bt.trace && pivots < Bt.trace_cap) {
+                    int *tr = Bt.trace + ((size_t)lp * Bt.trace_cap + pivots) * 3;
+                    tr[0] = primal_step ? 0 : 1;
+                    tr[1] = leaving;
+                    tr[2] = entering;
+                }
+            }
+            {
+                const unsigned long long w = (unsigned long long)(primal_step ? 0u : 1u) |
+                                             ((unsigned long long)(unsigned)leaving << 1) |
+                                             ((unsigned long long)(unsigned)entering << 32);
+                hash = (hash ^ w) * 0x100000001b3ULL;
+            }
+            ++pivots;
+            if (primal_step) ++n_primal;
+            __syncthreads();
+        }
+
+        // ---- results: objective_value / solution, simplex.rs:345-371 ----
+        __syncthreads();
+        if (tid == 0) {
+            double obj = 0.0;
+            for (int p = 0; p < M; ++p)
+                obj = __dadd_rn(obj, __dmul_rn(load_ref(theta, T.c_ref[c.bas[p]]), c.x[p]));
+            obj = __dadd_rn(load_ref(theta, T.c0_ref), obj);
+            Bt.status[lp] = status;
+            Bt.pivots[lp] = (int)pivots;
+            Bt.n_primal[lp] = (int)n_primal;
+            Bt.trace_hash[lp] = hash;
+            Bt.objective[lp] = obj;
+        }
+        if (Bt.x_basic)
+            for (int p = tid; p < M; p += c.nthreads) Bt.x_basic[(size_t)lp * M + p] = c.x[p];
+        if (Bt.basis)
+            for (int p = tid; p < M; p += c.nthreads) Bt.basis[(size_t)lp * M + p] = c.bas[p];
+        if (Bt.values) {
+            // position of each basic column, reusing posOf as scratch over columns is not
+            // possible (n_int > M), so search: n_orig*M/threads compares, once per LP.
+            for (int v = tid; v < T.n_orig; v += c.nthreads) {
+                const int cp = T.pos_index[v], cn = T.neg_index[v];
+                double pos = 0.0, neg = 0.0;
+                for (int p = 0; p < M; ++p) {
+                    const int col = c.bas[p];
+                    if (col == cp) pos = c.x[p];
+                    if (col == cn) neg = c.x[p];
+                }
+                Bt.values[(size_t)lp * T.n_orig + v] = __dsub_rn(pos, neg);
+            }
+        }
+        if (Bt.work) {
+            // per-LP executed flop counts (block sum via atomics on the output row)
+            double *w = Bt.work + (size_t)lp * 4;
+            if (c.n_lu) atomicAdd(&w[0], (double)c.n_lu);
+            if (c.n_solve) atomicAdd(&w[1], (double)c.n_solve);
+            if (c.n_price) atomicAdd(&w[2], (double)c.n_price);
+            if (tid == 0) atomicAdd(&w[3], (double)n_upd);
+        }
+    }
+}
+
+size_t smem_bytes_for(int M, int Nn, bool w_in_smem) {
+    const size_t S = (size_t)((M + 1) | 1);
+    size_t doubles = (w_in_smem ? (size_t)M * S : 0) + 4 * (size_t)M + 3 * (size_t)Nn +
+                     2 * 4 * kMaxWarps;
+    size_t ints = 7 * (size_t)M + (size_t)Nn + 2 * 4 * kMaxWarps + 8;
+    return doubles * 8 + ints * 4 + 16;
+}
+
+template <int TPR, bool WS>
+cudaError_t launch_one(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan,
+                       cudaStream_t st) {
+    auto kern = dz_batch_kernel<TPR, WS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         plan.smem_bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<plan.grid, plan.block, plan.smem_bytes, st>>>(T, Bt);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t tpr_hint, int32_t cps_hint,
+                LaunchPlan *plan, std::string *err) {
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        *err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return DZ_ERR_CUDA;
+    }
+    if (M >= 65535) {
+        *err = "batched kernel supports m_int < 65535";
+        return DZ_ERR_LIMIT;
+    }
+    const int MP = std::max(32, (M + 31) & ~31);
+    int tpr = tpr_hint > 0 ? tpr_hint : (MP <= 128 ? 4 : (MP <= 256 ? 2 : 1));
+    while (tpr > 1 && tpr * MP + 32 > 1024) tpr >>= 1;
+    if (tpr != 1 && tpr != 2 && tpr != 4) tpr = 1;
+    if (MP + 32 > 1024) {
+        *err = "batched kernel supports m_int <= 992 (one worker thread per basis row)";
+        return DZ_ERR_LIMIT;
+    }
+    const size_t max_smem = prop.sharedMemPerBlockOptin;
+    const size_t per_sm = prop.sharedMemPerMultiprocessor;
+    const size_t with_w = smem_bytes_for(M, Nn, true);
+    plan->tpr = tpr;
+    plan->block = tpr * MP + 32;
+    if (with_w <= max_smem) {
+        plan->w_in_smem = true;
+        plan->smem_bytes = (int32_t)with_w;
+        plan->gws_doubles_per_cta = 0;
+    } else {
+        plan->w_in_smem = false;
+        const size_t without = smem_bytes_for(M, Nn, false);
+        if (without > max_smem) {
+            *err = "problem too large for the batched kernel's shared-memory state";
+            return DZ_ERR_LIMIT;
+        }
+        plan->smem_bytes = (int32_t)without;
+        plan->gws_doubles_per_cta = (int64_t)M * ((M + 1) | 1);
+    }
+    int cps = (int)(per_sm / ((size_t)plan->smem_bytes + 1024));
+    cps = std::max(1, std::min(cps, 2048 / plan->block));
+    cps = std::min(cps, 32);
+    if (cps_hint > 0) cps = std::min(cps, cps_hint);
+    plan->ctas_per_sm = cps;
+    int64_t grid = (int64_t)prop.multiProcessorCount * cps;
+    if (grid > B) grid = B;
+    if (grid < 1) grid = 1;
+    plan->grid = (int32_t)grid;
+    return DZ_OK;
+}
+
+int launch_batch(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan, void *stream,
+                 std::string *err) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+#define DZ_LAUNCH(TPR)                                                                            \
+    e = plan.w_in_smem ? launch_one<TPR, true>(T, Bt, plan, st)                                   \
+                       : launch_one<TPR, false>(T, Bt, plan, st)
+    switch (plan.tpr) {
+    case 4: DZ_LAUNCH(4); break;
+    case 2: DZ_LAUNCH(2); break;
+    default: DZ_LAUNCH(1); break;
+    }
+#undef DZ_LAUNCH
+    if (e != cudaSuccess) {
+        *err = std::string("dz_batch_kernel launch: ") + cudaGetErrorString(e);
+        return DZ_ERR_CUDA;
+    }
+    return DZ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// FP64 pipe micro-benchmark: the roofline denominator for the exact path.
+// ---------------------------------------------------------------------------
+namespace {
+template <bool FUSED> __global__ void fp64_peak_kernel(double *out, int iters) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-9, a2 = a0 + 2e-9, a3 = a0 + 3e-9;
+    double a4 = a0 + 4e-9, a5 = a0 + 5e-9, a6 = a0 + 6e-9, a7 = a0 + 7e-9;
+    const double m = 1.0 - 1e-12, s = 1e-13;
+    for (int i = 0; i < iters; ++i) {
+        if (FUSED) {
+            a0 = __fma_rn(a0, m, -s), a1 = __fma_rn(a1, m, -s), a2 = __fma_rn(a2, m, -s);
+            a3 = __fma_rn(a3, m, -s), a4 = __fma_rn(a4, m, -s), a5 = __fma_rn(a5, m, -s);
+            a6 = __fma_rn(a6, m, -s), a7 = __fma_rn(a7, m, -s);
+        } else {
+            a0 = __dsub_rn(__dmul_rn(a0, m), s), a1 = __dsub_rn(__dmul_rn(a1, m), s);
+            a2 = __dsub_rn(__dmul_rn(a2, m), s), a3 = __dsub_rn(__dmul_rn(a3, m), s);
+            a4 = __dsub_rn(__dmul_rn(a4, m), s), a5 = __dsub_rn(__dmul_rn(a5, m), s);
+            a6 = __dsub_rn(__dmul_rn(a6, m), s), a7 = __dsub_rn(__dmul_rn(a7, m), s);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+} // namespace
+
+int measure_fp64_peak(int device, double *mul_sub_gflops, double *fma_gflops, std::string *err) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        *err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return DZ_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int block = 512, grid = prop.multiProcessorCount * 4, iters = 20000;
+    double *out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * (size_t)grid * block) != cudaSuccess) {
+        *err = "cudaMalloc failed";
+        return DZ_ERR_ALLOC;
+    }
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double res[2] = {0, 0};
+    for (int fused = 0; fused < 2; ++fused) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(a);
+            if (fused)
+                fp64_peak_kernel<true><<<grid, block>>>(out, iters);
+            else
+                fp64_peak_kernel<false><<<grid, block>>>(out, iters);
+            cudaEventRecord(b);
+            cudaEventSynchronize(b);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, a, b);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double flop = 2.0 * 8.0 * (double)iters * (double)grid * block;
+        res[fused] = flop / (best * 1e-3) / 1e9;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        *err = std::string("fp64 peak kernel: ") + cudaGetErrorString(e);
+        return DZ_ERR_CUDA;
+    }
+    if (mul_sub_gflops) *mul_sub_gflops = res[0];
+    if (fma_gflops) *fma_gflops = res[1];
+    return DZ_OK;
+}
+
+} // namespace dz
