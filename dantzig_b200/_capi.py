@@ -57,6 +57,7 @@ class Options(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("max_pivots", C.c_int64), ("trace_cap", C.c_int32),
         ("threads_per_row", C.c_int32), ("ctas_per_sm", C.c_int32), ("stream", C.c_void_p),
+        ("profile", C.c_int32),
     ]
 
 
@@ -65,7 +66,7 @@ class BatchResult(C.Structure):
         ("status", C.c_void_p), ("pivots", C.c_void_p), ("n_primal", C.c_void_p),
         ("trace_hash", C.c_void_p), ("objective", C.c_void_p), ("values", C.c_void_p),
         ("x_basic", C.c_void_p), ("basis", C.c_void_p), ("trace", C.c_void_p),
-        ("work", C.c_void_p),
+        ("work", C.c_void_p), ("prof", C.c_void_p),
     ]
 
 

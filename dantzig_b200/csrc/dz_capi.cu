@@ -110,7 +110,7 @@ struct dz_batch {
     // pinned staging for the download
     unsigned char *h_out = nullptr;
     size_t off_status = 0, off_pivots = 0, off_nprimal = 0, off_hash = 0, off_obj = 0,
-           off_values = 0, off_x = 0, off_basis = 0, off_trace = 0, off_work = 0;
+           off_values = 0, off_x = 0, off_basis = 0, off_trace = 0, off_work = 0, off_prof = 0;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -272,6 +272,7 @@ int dz_batch_create(const dz_template *tc, int64_t B, const dz_options *opt, dz_
     b->off_basis = place(sizeof(int32_t) * (size_t)B * M);
     b->off_work = place(sizeof(double) * (size_t)B * 4);
     b->off_trace = place(sizeof(int32_t) * (size_t)B * tc3);
+    b->off_prof = place(b->opt.profile ? sizeof(int64_t) * (size_t)B * 16 : 0);
     b->out_bytes = off;
     const size_t theta_bytes = sizeof(double) * (size_t)B * (size_t)h.n_theta;
     if (cudaMalloc(&b->d_theta, std::max<size_t>(theta_bytes, 8)) != cudaSuccess ||
@@ -306,6 +307,7 @@ int dz_batch_create(const dz_template *tc, int64_t B, const dz_options *opt, dz_
     bd.basis = reinterpret_cast<int32_t *>(b->d_out + b->off_basis);
     bd.work = reinterpret_cast<double *>(b->d_out + b->off_work);
     bd.trace = tc3 ? reinterpret_cast<int32_t *>(b->d_out + b->off_trace) : nullptr;
+    bd.prof = b->opt.profile ? reinterpret_cast<long long *>(b->d_out + b->off_prof) : nullptr;
     bd.next_lp = b->d_counter;
     bd.gws = b->d_gws;
     bd.gws_stride = b->plan.gws_doubles_per_cta;
@@ -390,6 +392,7 @@ int dz_batch_download(dz_batch *b, dz_batch_result *out) {
     DZ_CUDA(get(out->basis, b->off_basis, sizeof(int32_t) * B * M));
     DZ_CUDA(get(out->work, b->off_work, sizeof(double) * B * 4));
     if (tc3) DZ_CUDA(get(out->trace, b->off_trace, sizeof(int32_t) * B * tc3));
+    if (b->opt.profile) DZ_CUDA(get(out->prof, b->off_prof, sizeof(int64_t) * B * 16));
     DZ_CUDA(cudaStreamSynchronize(b->stream));
     return DZ_OK;
 }

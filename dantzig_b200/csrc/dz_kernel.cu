@@ -73,25 +73,30 @@ template <int N> struct Cand {
 // Block-wide arg-max of N independent (key, idx) candidates with one barrier.
 // red_key/red_idx hold [2][N][kMaxWarps]; `parity` alternates between calls so
 // a slot is never rewritten before every thread has read it.
+// Only warps 0..nparts-1 hold candidates (warp-uniform), the others just wait
+// for the result.
 template <int N>
 __device__ __forceinline__ void block_argmax(Cand<N> &c, double *red_key, int *red_idx,
-                                             int &parity, int nwarps) {
+                                             int &parity, int nparts) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = nparts;
+    if (warp < nparts) {
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
+        for (int n = 0; n < N; ++n) {
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double k2 = __shfl_xor_sync(kFull, c.key[n], off);
-            const int i2 = __shfl_xor_sync(kFull, c.idx[n], off);
-            if (beats(k2, i2, c.key[n], c.idx[n])) {
-                c.key[n] = k2;
-                c.idx[n] = i2;
+            for (int off = 16; off > 0; off >>= 1) {
+                const double k2 = __shfl_xor_sync(kFull, c.key[n], off);
+                const int i2 = __shfl_xor_sync(kFull, c.idx[n], off);
+                if (beats(k2, i2, c.key[n], c.idx[n])) {
+                    c.key[n] = k2;
+                    c.idx[n] = i2;
+                }
             }
         }
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *rk = red_key + (size_t)parity * N * kMaxWarps;
     int *ri = red_idx + (size_t)parity * N * kMaxWarps;
-    if (lane == 0) {
+    if (lane == 0 && warp < nparts) {
 #pragma unroll
         for (int n = 0; n < N; ++n) {
             rk[n * kMaxWarps + warp] = c.key[n];
@@ -126,11 +131,28 @@ struct Ctx {
     double *red_key;
     int *bas, *nb, *rowAt, *posOf, *cnt, *unitRow, *retired, *pend, *red_idx, *ctl;
     int parity;
+    // optional phase timing (thread 0 accumulates clock64 deltas into shared memory)
+    long long *prof;
+    long long t_last;
     // counters (per thread)
     unsigned long long n_lu, n_solve, n_price;
 };
 
 enum { CTL_K = 0, CTL_FLAG = 1, CTL_LP = 2 };
+
+// Phase slots of the optional per-LP cycle profile (BatchDev::prof).
+enum {
+    PH_STATUS = 0, PH_GATHER = 1, PH_ELIM = 2, PH_BACK_A = 3, PH_BACK_B = 4, PH_PRICE = 5,
+    PH_RATIO = 6, PH_UPDATE = 7, PH_NONTRIVIAL = 8, PH_PENDING = 9, PH_SOLVES = 10, PH_COUNT = 16
+};
+
+__device__ __forceinline__ void tick(Ctx &c, int slot) {
+    if (c.prof && threadIdx.x == 0) {
+        const long long now = clock64();
+        c.prof[slot] += now - c.t_last;
+        c.t_last = now;
+    }
+}
 
 // find_first_pivot (simplex.rs:423-437) for both the dual (z) and primal (x)
 // sides with a single barrier.  Returns positions (-1 = None).  The reference's
@@ -228,6 +250,7 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
         }
     }
     __syncthreads();
+    tick(c, PH_BACK_A);
     if (!worker) { // control warp
         const int lane = tid - c.NW;
         for (int base = (M - 1) & ~31; base >= 0; base -= 32) {
@@ -237,6 +260,7 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
                 const int bit = 31 - __clz(pm);
                 pm &= ~(1u << bit);
                 const int i = base + bit;
+                if (c.prof && lane == 0) c.prof[PH_PENDING] += 1;
                 const double *row = W + (size_t)c.rowAt[i] * S;
                 double s = row[M];
                 for (int j0 = i + 1; j0 < M; j0 += 32) {
@@ -266,6 +290,7 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
         }
     }
     __syncthreads();
+    tick(c, PH_BACK_B);
 }
 
 // lu_solve (linalg.rs:8-10) of B (transposed == false, rhs = column `arg` of A)
@@ -281,8 +306,10 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
 
     // ---- gather: W = dense(B) or dense(B^T), rhs in column M ----------------
     {
-        const int total = M * S;
-        for (int e = tid; e < total; e += c.nthreads) W[e] = 0.0;
+        const int total = M * S; // W is 16-byte aligned in both homes
+        double2 *W2 = reinterpret_cast<double2 *>(W);
+        for (int e = tid; e < (total >> 1); e += c.nthreads) W2[e] = make_double2(0.0, 0.0);
+        if ((total & 1) && tid == 0) W[total - 1] = 0.0;
         for (int i = tid; i < M; i += c.nthreads) {
             c.cnt[i] = 0;
             c.unitRow[i] = -1;
@@ -327,6 +354,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
         W[(size_t)arg * S + M] = 1.0;
     }
     __syncthreads();
+    tick(c, PH_GATHER);
 
     // ---- elimination ---------------------------------------------------------
     int k = 0;
@@ -379,24 +407,40 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                 }
             }
         }
-        block_argmax<1>(cd, c.red_key, c.red_idx, c.parity, c.nwarps);
+        block_argmax<1>(cd, c.red_key, c.red_idx, c.parity, c.MP >> 5);
         const int pr = cd.idx[0] & 0xffff, ppos = cd.idx[0] >> 16;
         const double pv = W[(size_t)pr * S + k];
-        if (pv != 0.0 && active && r != pr && v != 0.0) {
-            const double l = __ddiv_rn(v, pv);
-            const double *prow = W + (size_t)pr * S;
-            double *myrow = W + (size_t)r * S;
-            unsigned nupd = 0;
-            for (int j = k + 1 + h; j <= M; j += TPR) {
-                const double u = prow[j];
-                if (u != 0.0) {
-                    myrow[j] = __dsub_rn(myrow[j], __dmul_rn(l, u));
-                    ++nupd;
+        if (pv != 0.0 && worker) {
+            // rows with a zero multiplier are untouched (the pivot row is finite)
+            const bool need = active && r != pr && v != 0.0;
+            if (__any_sync(kFull, need)) {
+                const double l = need ? __ddiv_rn(v, pv) : 0.0;
+                const double *prow = W + (size_t)pr * S;
+                double *myrow = W + (size_t)r * S;
+                const int lane = tid & 31;
+                unsigned nupd = 0;
+                // the pivot row is read once per warp, 32 columns at a time; its nonzero
+                // columns are broadcast lane by lane (exact zeros of u are no-ops)
+                for (int c0 = k + 1 + 32 * h; c0 <= M; c0 += 32 * TPR) {
+                    const int jl = c0 + lane;
+                    const double ul = (jl <= M) ? prow[jl] : 0.0;
+                    unsigned mk = __ballot_sync(kFull, ul != 0.0);
+                    nupd += __popc(mk);
+                    while (mk) {
+                        const int b = __ffs(mk) - 1;
+                        mk &= mk - 1;
+                        const double u = __shfl_sync(kFull, ul, b);
+                        if (need) {
+                            const int j = c0 + b;
+                            myrow[j] = __dsub_rn(myrow[j], __dmul_rn(l, u));
+                        }
+                    }
                 }
+                if (need) c.n_lu += 2ull * nupd + (h == 0 ? 1 : 0);
             }
-            c.n_lu += 2ull * nupd + (h == 0 ? 1 : 0);
         }
         if (tid == c.NW) { // record the interchange k <-> ppos
+            if (c.prof) c.prof[PH_NONTRIVIAL] += 1;
             const int rk = c.rowAt[k];
             c.rowAt[k] = pr;
             c.rowAt[ppos] = rk;
@@ -406,6 +450,8 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
         }
         ++k;
     }
+    tick(c, PH_ELIM);
+    if (c.prof && tid == 0) c.prof[PH_SOLVES] += 1;
     // ---- back substitution ------------------------------------------------------
     back_substitute<TPR>(c, y, false);
     if (c.ctl[CTL_FLAG]) {
@@ -445,6 +491,8 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
         c.zb = dp, dp += Nn;
         c.dzv = dp, dp += Nn;
         c.red_key = dp, dp += 2 * 4 * kMaxWarps;
+        c.prof = Bt.prof ? reinterpret_cast<long long *>(dp) : nullptr;
+        dp += PH_COUNT;
         int *ip = reinterpret_cast<int *>(dp);
         c.bas = ip, ip += M;
         c.nb = ip, ip += Nn;
@@ -468,6 +516,10 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
         const double *__restrict__ theta = Bt.theta + (size_t)lp * Bt.n_theta;
         c.n_lu = c.n_solve = c.n_price = 0;
         unsigned long long n_upd = 0;
+        if (c.prof) {
+            if (tid < PH_COUNT) c.prof[tid] = 0;
+            c.t_last = clock64();
+        }
 
         // initial state (simplex.rs:190-205)
         for (int p = tid; p < M; p += c.nthreads) {
@@ -492,6 +544,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
             // ---- status(), simplex.rs:274-306 ----
             int q0, p0;
             find_first_both(c, q0, p0);
+            tick(c, PH_STATUS);
             bool primal_step;
             double mu;
             if (q0 >= 0 && p0 >= 0) {
@@ -524,6 +577,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
                 q = q0;
                 basis_solve<TPR>(c, T, theta, false, c.nb[q], c.dxv);
                 p = find_second(c, mu, c.x, c.xb, c.dxv, M);
+                tick(c, PH_RATIO);
                 if (p < 0) {
                     status = DZ_UNBOUNDED;
                     break;
@@ -548,8 +602,10 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
                 c.dzv[k] = s;
             }
             __syncthreads();
+            tick(c, PH_PRICE);
             if (!primal_step) {
                 q = find_second(c, mu, c.z, c.zb, c.dzv, Nn);
+                tick(c, PH_RATIO);
                 if (q < 0) {
                     status = DZ_INFEASIBLE;
                     break;
@@ -614,6 +670,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
             ++pivots;
             if (primal_step) ++n_primal;
             __syncthreads();
+            tick(c, PH_UPDATE);
         }
 
         // ---- results: objective_value / solution, simplex.rs:345-371 ----
@@ -647,6 +704,10 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
                 Bt.values[(size_t)lp * T.n_orig + v] = __dsub_rn(pos, neg);
             }
         }
+        if (c.prof) {
+            __syncthreads();
+            if (tid < PH_COUNT) Bt.prof[(size_t)lp * PH_COUNT + tid] = c.prof[tid];
+        }
         if (Bt.work) {
             // per-LP executed flop counts (block sum via atomics on the output row)
             double *w = Bt.work + (size_t)lp * 4;
@@ -661,7 +722,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
 size_t smem_bytes_for(int M, int Nn, bool w_in_smem) {
     const size_t S = (size_t)((M + 1) | 1);
     size_t doubles = (w_in_smem ? (size_t)M * S : 0) + 4 * (size_t)M + 3 * (size_t)Nn +
-                     2 * 4 * kMaxWarps;
+                     2 * 4 * kMaxWarps + PH_COUNT;
     size_t ints = 7 * (size_t)M + (size_t)Nn + 2 * 4 * kMaxWarps + 8;
     return doubles * 8 + ints * 4 + 16;
 }
@@ -692,7 +753,7 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t tpr_hint, 
         return DZ_ERR_LIMIT;
     }
     const int MP = std::max(32, (M + 31) & ~31);
-    int tpr = tpr_hint > 0 ? tpr_hint : (MP <= 128 ? 4 : (MP <= 256 ? 2 : 1));
+    int tpr = tpr_hint > 0 ? tpr_hint : 1;
     while (tpr > 1 && tpr * MP + 32 > 1024) tpr >>= 1;
     if (tpr != 1 && tpr != 2 && tpr != 4) tpr = 1;
     if (MP + 32 > 1024) {

@@ -1,0 +1,243 @@
+// dz_rustmod.cpp -- the drop-in replacement for the reference's compiled
+// extension module `dantzig.rust` (/root/reference/src/lib.rs:29-38), written
+// as host C++ above the C ABI (include/dantzig_b200.h).
+//
+// It exports exactly the Python-visible surface of the pyo3 module:
+//   Variable(*, lb, ub)            id/lb/ub read-only; ids from a process-global
+//                                   counter                      pyobjs.rs:8-31
+//   PyLinExpr(coefs, vars)         map_ids_to_coefs, __neg__, __add__ (merge by
+//                                   id, first-appearance order), __mul__
+//                                                                pyobjs.rs:39-112
+//   PyAffExpr(*, linexpr, constant) getters pylinexpr, constant   pyobjs.rs:114-133
+//   PyInequality(*, linexpr, b)                                   pyobjs.rs:135-152
+//   PySolution                      objective_value, __getitem__ (0.0 for an
+//                                   unknown variable)             pyobjs.rs:154-175
+//   solve(objective, constraints)   lib.rs:16-27; raises
+//                                   dantzig.exceptions.UnboundedError /
+//                                   InfeasibleError with the reference's text.
+// The solve itself is dz_solve_model: host lowering + the CUDA kernels.  There
+// is no CPU path; without a GPU solve() raises RuntimeError.  A Rust panic of
+// the reference (safe_divide assert etc.) surfaces as dantzig_b200 PanicException
+// (a BaseException subclass, like pyo3_runtime.PanicException).
+
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <atomic>
+#include <cstdint>
+#include <optional>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/dantzig_b200.h"
+
+namespace py = pybind11;
+
+namespace {
+
+std::atomic<std::size_t> g_counter{0}; // pyobjs.rs:8
+
+struct Variable {
+    std::size_t id;
+    std::optional<double> lb, ub;
+    Variable(std::optional<double> lb_, std::optional<double> ub_)
+        : id(g_counter.fetch_add(1, std::memory_order_relaxed)), lb(lb_), ub(ub_) {}
+};
+
+struct LinExpr {
+    std::vector<double> coefs;
+    std::vector<Variable> vars;
+    std::unordered_map<std::size_t, std::size_t> id_to_index;
+
+    LinExpr(std::vector<double> c, std::vector<Variable> v) : coefs(std::move(c)), vars(std::move(v)) {
+        for (std::size_t i = 0; i < vars.size(); ++i) id_to_index[vars[i].id] = i; // later wins
+    }
+    py::dict map_ids_to_coefs() const { // pyobjs.rs:62-69 (later duplicate wins)
+        py::dict d;
+        for (std::size_t i = 0; i < coefs.size() && i < vars.size(); ++i)
+            d[py::int_(vars[i].id)] = coefs[i];
+        return d;
+    }
+    LinExpr neg() const { // pyobjs.rs:71-76
+        LinExpr r(*this);
+        for (auto &c : r.coefs) c = -c;
+        return r;
+    }
+    LinExpr add(const LinExpr &o) const { // pyobjs.rs:78-104
+        LinExpr r(*this);
+        for (std::size_t i = 0; i < o.coefs.size() && i < o.vars.size(); ++i) {
+            auto it = r.id_to_index.find(o.vars[i].id);
+            if (it != r.id_to_index.end()) {
+                r.coefs[it->second] += o.coefs[i];
+            } else {
+                r.id_to_index.emplace(o.vars[i].id, r.vars.size());
+                r.vars.push_back(o.vars[i]);
+                r.coefs.push_back(o.coefs[i]);
+            }
+        }
+        return r;
+    }
+    LinExpr mul(double k) const { // pyobjs.rs:106-111, model.rs:31-36
+        LinExpr r(*this);
+        for (auto &c : r.coefs) c = k * c;
+        return r;
+    }
+};
+
+struct AffExpr {
+    LinExpr linexpr;
+    double constant;
+};
+struct Inequality {
+    LinExpr linexpr;
+    double b;
+};
+struct Solution {
+    double objective_value;
+    std::unordered_map<std::size_t, double> values;
+    int32_t pivots;
+    uint64_t trace_hash;
+};
+
+// Flatten (objective, constraints) into the dz_model arrays: a variable table
+// keyed by Variable.id in first-appearance order, terms in their given order.
+struct Flat {
+    std::vector<std::size_t> ids;
+    std::unordered_map<std::size_t, int32_t> index;
+    std::vector<uint8_t> has_lb, has_ub;
+    std::vector<double> lb, ub;
+    std::vector<int32_t> obj_var, row_var;
+    std::vector<double> obj_coef, row_coef, rhs;
+    std::vector<int64_t> row_ptr{0};
+
+    int32_t var(const Variable &v) {
+        auto it = index.find(v.id);
+        if (it != index.end()) return it->second; // bounds of the first occurrence (simplex.rs:134)
+        const int32_t k = (int32_t)ids.size();
+        index.emplace(v.id, k);
+        ids.push_back(v.id);
+        has_lb.push_back(v.lb.has_value());
+        has_ub.push_back(v.ub.has_value());
+        lb.push_back(v.lb.value_or(0.0));
+        ub.push_back(v.ub.value_or(0.0));
+        return k;
+    }
+};
+
+Solution solve(const AffExpr &objective, const std::vector<Inequality> &constraints) {
+    Flat f;
+    const std::size_t n_obj = std::min(objective.linexpr.coefs.size(), objective.linexpr.vars.size());
+    for (std::size_t i = 0; i < n_obj; ++i) {
+        f.obj_var.push_back(f.var(objective.linexpr.vars[i]));
+        f.obj_coef.push_back(objective.linexpr.coefs[i]);
+    }
+    for (const auto &c : constraints) {
+        const std::size_t n = std::min(c.linexpr.coefs.size(), c.linexpr.vars.size());
+        for (std::size_t i = 0; i < n; ++i) {
+            f.row_var.push_back(f.var(c.linexpr.vars[i]));
+            f.row_coef.push_back(c.linexpr.coefs[i]);
+        }
+        f.row_ptr.push_back((int64_t)f.row_var.size());
+        f.rhs.push_back(c.b);
+    }
+    dz_model m{};
+    m.n_vars = (int32_t)f.ids.size();
+    m.has_lb = f.has_lb.data();
+    m.has_ub = f.has_ub.data();
+    m.lb = f.lb.data();
+    m.ub = f.ub.data();
+    m.n_obj = (int32_t)f.obj_var.size();
+    m.obj_var = f.obj_var.data();
+    m.obj_coef = f.obj_coef.data();
+    m.obj_const = objective.constant;
+    m.n_rows = (int32_t)f.rhs.size();
+    m.row_ptr = f.row_ptr.data();
+    m.row_var = f.row_var.data();
+    m.row_coef = f.row_coef.data();
+    m.rhs = f.rhs.data();
+
+    dz_options opt;
+    dz_options_default(&opt);
+    dz_solution sol{};
+    std::vector<double> values(f.ids.size() + 1, 0.0);
+    int rc;
+    {
+        py::gil_scoped_release release; // the reference holds the GIL; we need not
+        rc = dz_solve_model(&m, &opt, &sol, values.data());
+    }
+    if (rc != DZ_OK)
+        throw std::runtime_error(std::string("dantzig_b200: ") + dz_last_error());
+    switch (sol.status) {
+    case DZ_OPTIMAL: break;
+    case DZ_UNBOUNDED: { // lib.rs:24
+        py::object exc = py::module_::import("dantzig.exceptions").attr("UnboundedError");
+        PyErr_SetString(exc.ptr(), "The objective is unbounded");
+        throw py::error_already_set();
+    }
+    case DZ_INFEASIBLE: { // lib.rs:25
+        py::object exc = py::module_::import("dantzig.exceptions").attr("InfeasibleError");
+        PyErr_SetString(exc.ptr(), "The model is infeasible");
+        throw py::error_already_set();
+    }
+    case DZ_BREAKDOWN: {
+        py::object exc = py::module_::import("dantzig.rust").attr("PanicException");
+        PyErr_SetString(exc.ptr(), "numerical breakdown: the reference solver panics on this model "
+                                   "(safe_divide / unexpected code path)");
+        throw py::error_already_set();
+    }
+    default:
+        throw std::runtime_error("dantzig_b200: pivot watchdog reached (the reference would not terminate)");
+    }
+    Solution s;
+    s.objective_value = sol.objective;
+    s.pivots = sol.pivots;
+    s.trace_hash = sol.trace_hash;
+    for (std::size_t k = 0; k < f.ids.size(); ++k) s.values[f.ids[k]] = values[k];
+    return s;
+}
+
+} // namespace
+
+PYBIND11_MODULE(rust, m) {
+    m.attr("__name__") = "dantzig.rust"; // pyclass(module = "dantzig.rust")
+    m.doc() = "B200-native drop-in for dantzig's compiled solver module";
+
+    // PanicException derives from BaseException like pyo3_runtime.PanicException
+    m.attr("PanicException") = py::reinterpret_steal<py::object>(
+        PyErr_NewException("dantzig.rust.PanicException", PyExc_BaseException, nullptr));
+
+    py::class_<Variable>(m, "Variable")
+        .def(py::init<std::optional<double>, std::optional<double>>(), py::kw_only(), py::arg("lb"),
+             py::arg("ub"))
+        .def_readonly("id", &Variable::id)
+        .def_readonly("lb", &Variable::lb)
+        .def_readonly("ub", &Variable::ub);
+
+    py::class_<LinExpr>(m, "PyLinExpr")
+        .def(py::init<std::vector<double>, std::vector<Variable>>(), py::arg("coefs"), py::arg("vars"))
+        .def("map_ids_to_coefs", &LinExpr::map_ids_to_coefs)
+        .def("__neg__", &LinExpr::neg)
+        .def("__add__", &LinExpr::add)
+        .def("__mul__", &LinExpr::mul);
+
+    py::class_<AffExpr>(m, "PyAffExpr")
+        .def(py::init([](const LinExpr &l, double c) { return AffExpr{l, c}; }), py::kw_only(),
+             py::arg("linexpr"), py::arg("constant"))
+        .def_property_readonly("pylinexpr", [](const AffExpr &a) { return a.linexpr; })
+        .def_readonly("constant", &AffExpr::constant);
+
+    py::class_<Inequality>(m, "PyInequality")
+        .def(py::init([](const LinExpr &l, double b) { return Inequality{l, b}; }), py::kw_only(),
+             py::arg("linexpr"), py::arg("b"));
+
+    py::class_<Solution>(m, "PySolution")
+        .def_readonly("objective_value", &Solution::objective_value)
+        .def_readonly("pivots", &Solution::pivots)         // extension: not in the reference
+        .def_readonly("trace_hash", &Solution::trace_hash) // extension
+        .def("__getitem__", [](const Solution &s, const Variable &v) {
+            auto it = s.values.find(v.id);
+            return it == s.values.end() ? 0.0 : it->second; // pyobjs.rs:163-165
+        });
+
+    m.def("solve", &solve, py::arg("objective"), py::arg("constraints"));
+}

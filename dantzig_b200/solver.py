@@ -93,14 +93,17 @@ class BatchResult:
     basis: np.ndarray | None
     trace: np.ndarray | None
     work: np.ndarray        # [B, 4] executed flops: LU, solves, pricing, updates
+    prof: np.ndarray | None = None  # [B, 16] phase cycles (profile=True)
 
 
-def _options(device=0, max_pivots=0, trace_cap=0, threads_per_row=0, ctas_per_sm=0, stream=None):
+def _options(device=0, max_pivots=0, trace_cap=0, threads_per_row=0, ctas_per_sm=0, stream=None,
+             profile=False):
     o = _capi.Options()
     _capi.lib().dz_options_default(C.byref(o))
     o.device, o.max_pivots, o.trace_cap = int(device), int(max_pivots), int(trace_cap)
     o.threads_per_row, o.ctas_per_sm = int(threads_per_row), int(ctas_per_sm)
     o.stream = stream
+    o.profile = 1 if profile else 0
     return o
 
 
@@ -109,11 +112,11 @@ class Batch:
 
     def __init__(self, template: Template, B: int, *, device: int = 0, max_pivots: int = 0,
                  trace_cap: int = 0, threads_per_row: int = 0, ctas_per_sm: int = 0,
-                 stream: int | None = None, want_basis: bool = False):
+                 stream: int | None = None, want_basis: bool = False, profile: bool = False):
         self.template, self.B = template, int(B)
-        self.trace_cap, self.want_basis = int(trace_cap), want_basis
+        self.trace_cap, self.want_basis, self.profile = int(trace_cap), want_basis, profile
         self._h = C.c_void_p()
-        o = _options(device, max_pivots, trace_cap, threads_per_row, ctas_per_sm, stream)
+        o = _options(device, max_pivots, trace_cap, threads_per_row, ctas_per_sm, stream, profile)
         _capi.check(_capi.lib().dz_batch_create(template.handle, self.B, C.byref(o),
                                                 C.byref(self._h)))
 
@@ -173,10 +176,11 @@ class Batch:
             basis=None if light else np.zeros((B, t.m), np.int32),
             trace=None if (light or not self.trace_cap) else np.zeros((B, self.trace_cap, 3), np.int32),
             work=np.zeros((B, 4), np.float64),
+            prof=np.zeros((B, 16), np.int64) if self.profile else None,
         )
         r = _capi.BatchResult()
         for name in ("status", "pivots", "n_primal", "trace_hash", "objective", "values",
-                     "x_basic", "basis", "trace", "work"):
+                     "x_basic", "basis", "trace", "work", "prof"):
             a = getattr(res, name)
             setattr(r, name, None if a is None else a.ctypes.data)
         _capi.check(_capi.lib().dz_batch_download(self._h, C.byref(r)))

@@ -127,6 +127,7 @@ typedef struct dz_options {
     int32_t threads_per_row; /* 0 = auto; kernel tuning knob, never changes results   */
     int32_t ctas_per_sm;  /* 0 = auto                                                  */
     void *stream;         /* cudaStream_t to launch on (NULL = the library's stream)   */
+    int32_t profile;      /* 1 = record per-LP phase cycle counts (dz_batch_result.prof) */
 } dz_options;
 void dz_options_default(dz_options *o);
 
@@ -143,6 +144,7 @@ typedef struct dz_batch_result {
     int32_t *basis;       /* [B][m]      final basic column per position                */
     int32_t *trace;       /* [B][trace_cap][3] (kind 0=primal 1=dual, leaving, entering)*/
     double *work;         /* [B][4] executed flops: LU, solves, pricing, updates        */
+    int64_t *prof;        /* [B][16] SM cycles per phase + step counters (opt.profile)  */
 } dz_batch_result;
 
 /* ---- NEW batched entry point: host buffers in, host buffers out -------------

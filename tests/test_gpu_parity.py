@@ -1,0 +1,200 @@
+"""Parity of the CUDA path with the oracle, called through the C ABI.
+Bit-exact: status, pivot count, pivot trace (hash and entries), objective bits,
+primal values.  Run on the B200 box:  pytest -m gpu"""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from dantzig_b200 import Batch, Template, generate, solve_batch, solve_model
+from dantzig_b200.model import model_from_theta
+from tests import cases, kat
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STATUS = {"optimal": 0, "unbounded": 1, "infeasible": 2}
+
+
+def bits(x):
+    return struct.pack("<d", float(x)).hex()
+
+
+def sha(a):
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+# ---- the reference's own known-answer tests through dz_solve_model --------------
+@pytest.mark.parametrize("name,model,expect", kat.rust_kats(), ids=[k[0] for k in kat.rust_kats()])
+def test_rust_kats_on_device(oracle, name, model, expect):
+    s = solve_model(model)
+    assert s.status == STATUS[expect[0]]
+    o = oracle.lower(model).solve(oracle.LITERAL)
+    assert (s.pivots, s.trace_hash) == (o.pivots, o.trace_hash)
+    if expect[0] == "optimal":
+        assert abs(s.objective - expect[1]) <= 1e-12          # src/simplex.rs:477-482
+        assert bits(s.objective) == bits(o.objective)
+        for v, val in expect[2].items():
+            assert abs(s.values[v] - val) <= 1e-12
+
+
+@pytest.mark.parametrize("name,model,minimize,expect", kat.python_kats(),
+                         ids=[k[0] for k in kat.python_kats()])
+def test_python_kats_on_device(name, model, minimize, expect):
+    s = solve_model(model)
+    assert s.status == STATUS[expect[0]]
+    if expect[0] == "optimal":                                   # exact ==, tests/test_optimize.py
+        assert (-s.objective if minimize else s.objective) == expect[1]
+        for v, val in expect[2].items():
+            assert s.values[v] == val
+
+
+@pytest.mark.parametrize("name,model", cases.ragged_models(), ids=[c[0] for c in cases.ragged_models()])
+def test_ragged_models_on_device(oracle, name, model):
+    s = solve_model(model)
+    lo = oracle.lower(model)
+    o = lo.solve(oracle.LITERAL)
+    assert (s.status, s.pivots, s.trace_hash, bits(s.objective)) == (
+        o.status, o.pivots, o.trace_hash, bits(o.objective))
+    for k, v in enumerate(lo.orig_var):
+        assert bits(s.values[v]) == bits(o.values[k])
+
+
+def test_empty_basis_is_breakdown():
+    from dantzig_b200.model import ModelBuilder
+
+    mb = ModelBuilder()
+    x = mb.free()
+    mb.maximize([(1.0, x)])
+    assert solve_model(mb.build()).status == 3                   # the reference panics
+
+
+# ---- batched kernel against the live oracle and the committed fixtures ----------
+def _check_batch(oracle, w, res, n_oracle, variant):
+    for i in range(min(n_oracle, w.B)):
+        o = oracle.lower(model_from_theta(w.structure, w.theta[i])).solve(variant, trace_cap=res.trace.shape[1])
+        assert (res.status[i], res.pivots[i], res.n_primal[i], int(res.trace_hash[i])) == (
+            o.status, o.pivots, o.n_primal, o.trace_hash), i
+        assert np.array_equal(res.trace[i, : min(o.pivots, res.trace.shape[1])], o.trace), i
+        assert bits(res.objective[i]) == bits(o.objective), i
+        assert np.array_equal(res.values[i].view(np.uint64), o.values.view(np.uint64)), i
+        assert np.array_equal(res.x_basic[i].view(np.uint64), o.x_basic.view(np.uint64)), i
+        assert np.array_equal(res.basis[i], o.basis), i
+
+
+@pytest.mark.parametrize("wl", sorted(cases.GOLDEN_WORKLOADS))
+@pytest.mark.parametrize("tpr", [0, 2])
+def test_batch_parity(oracle, wl, tpr):
+    w = cases.GOLDEN_WORKLOADS[wl]()
+    t = Template(w.structure)
+    res = solve_batch(t, w.theta, trace_cap=256, threads_per_row=tpr)
+    g = json.load(open(os.path.join(GOLD, wl + ".json")))
+    assert sha(w.theta) == g["theta_sha"]
+    for i, e in enumerate(g["lps"]):                             # every LP against the fixture
+        assert (res.status[i], res.pivots[i], res.n_primal[i], int(res.trace_hash[i])) == (
+            e["status"], e["pivots"], e["n_primal"], e["trace_hash"]), i
+        assert bits(res.objective[i]) == e["objective_bits"], i
+        assert sha(res.values[i]) == e["values_sha"], i
+    big = w.m >= 60
+    _check_batch(oracle, w, res, 2 if big else 12, oracle.SKIP if big else oracle.LITERAL)
+
+
+def test_batch_order_and_resolve_invariance():
+    """Solving is a pure function of each LP: permuting the batch permutes the
+    results, re-solving a resident batch reproduces them bit for bit."""
+    w = generate.config2(96)
+    t = Template(w.structure)
+    b = Batch(t, w.B)
+    b.upload(w.theta)
+    b.solve()
+    r1 = b.download()
+    b.solve()
+    r2 = b.download()
+    perm = np.random.default_rng(0).permutation(w.B)
+    r3 = solve_batch(t, w.theta[perm])
+    for name in ("status", "pivots", "trace_hash", "objective", "values", "x_basic", "basis"):
+        a1, a2, a3 = getattr(r1, name), getattr(r2, name), getattr(r3, name)
+        assert np.array_equal(a1, a2, equal_nan=a1.dtype.kind == "f"), name
+        assert np.array_equal(a1[perm], a3, equal_nan=a1.dtype.kind == "f"), name
+    b.close()
+
+
+def test_full_config2_properties(oracle):
+    """BASELINE.json configs[1] at full size: 4096 LPs.  Size-independent checks:
+    feasibility and complementary objective agreement via HiGHS on a sample,
+    a checksum of trace hashes stable across launch shapes, oracle parity on a
+    strided sample, and the three known false-unbounded LPs."""
+    from scipy.optimize import linprog
+
+    w = generate.config2(4096)
+    t = Template(w.structure)
+    r = solve_batch(t, w.theta)
+    r2 = solve_batch(t, w.theta, threads_per_row=4, ctas_per_sm=1)
+    assert np.array_equal(r.trace_hash, r2.trace_hash) and np.array_equal(r.objective, r2.objective)
+    assert sorted(np.flatnonzero(r.status != 0).tolist()) == [287, 2142, 3300]
+    assert (r.status[[287, 2142, 3300]] == 1).all()
+    m, n = w.m, w.n
+    for i in range(0, 4096, 512):
+        th = w.theta[i]
+        o = oracle.lower(model_from_theta(w.structure, th)).solve(oracle.SKIP)
+        assert (r.status[i], r.pivots[i], int(r.trace_hash[i]), bits(r.objective[i])) == (
+            o.status, o.pivots, o.trace_hash, bits(o.objective))
+        c = -th[2:2 + n]
+        A = th[2 + n:2 + n + m * n].reshape(m, n)
+        b = th[2 + n + m * n:2 + n + m * n + m]
+        x = r.values[i]
+        assert (x >= -1e-9).all() and (A @ x <= b + 1e-7).all()          # primal feasible
+        ref = linprog(c, A_ub=A, b_ub=b, bounds=[(0, None)] * n, method="highs")
+        assert abs(-r.objective[i] - ref.fun) <= 1e-9 * max(1.0, abs(ref.fun))
+        assert np.abs(x - ref.x).max() <= 1e-7
+
+
+def test_pivot_cap_is_reported():
+    w = generate.config2(4)
+    t = Template(w.structure)
+    r = solve_batch(t, w.theta, max_pivots=10)
+    assert (r.status == 4).all() and (r.pivots == 10).all()
+
+
+# ---- the drop-in extension module ----------------------------------------------------
+def test_rust_module_end_to_end():
+    import sys
+    import types
+
+    import dantzig_b200.rust as rs
+
+    exc = types.ModuleType("dantzig.exceptions")
+    exc.UnboundedError = type("UnboundedError", (Exception,), {})
+    exc.InfeasibleError = type("InfeasibleError", (Exception,), {})
+    had = {k: sys.modules.get(k) for k in ("dantzig", "dantzig.exceptions", "dantzig.rust")}
+    try:
+        if "dantzig.exceptions" not in sys.modules:
+            pkg = types.ModuleType("dantzig")
+            pkg.exceptions = exc
+            sys.modules["dantzig"], sys.modules["dantzig.exceptions"] = pkg, exc
+        sys.modules["dantzig.rust"] = rs
+        exc_mod = sys.modules["dantzig.exceptions"]
+        x, y = rs.Variable(lb=0.0, ub=None), rs.Variable(lb=0.0, ub=None)
+        # tests/test_optimize.py:4-11  min 2x-2y st y == 3  (negated for the max-form solver)
+        obj = rs.PyAffExpr(linexpr=rs.PyLinExpr([-2.0, 2.0], [x, y]), constant=-0.0)
+        rows = [rs.PyInequality(linexpr=rs.PyLinExpr([1.0], [y]), b=3.0),
+                rs.PyInequality(linexpr=rs.PyLinExpr([-1.0], [y]), b=-3.0)]
+        s = rs.solve(obj, rows)
+        assert -s.objective_value == -6.0 and s[x] == 0.0 and s[y] == 3.0
+        assert s[rs.Variable(lb=None, ub=None)] == 0.0               # unknown variable
+        with pytest.raises(exc_mod.UnboundedError, match="The objective is unbounded"):
+            rs.solve(rs.PyAffExpr(linexpr=rs.PyLinExpr([1.0], [x]), constant=0.0), [])
+        with pytest.raises(exc_mod.InfeasibleError, match="The model is infeasible"):
+            le = rs.PyLinExpr([1.0, 1.0], [x, y])
+            rs.solve(rs.PyAffExpr(linexpr=le, constant=0.0),
+                     [rs.PyInequality(linexpr=le, b=1.0), rs.PyInequality(linexpr=-le, b=-1.0),
+                      rs.PyInequality(linexpr=le, b=2.0), rs.PyInequality(linexpr=-le, b=-2.0)])
+    finally:
+        for k, v in had.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

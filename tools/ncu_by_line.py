@@ -1,0 +1,60 @@
+"""Aggregate an ncu report's per-instruction samples by CUDA source line.
+
+usage: ncu_by_line.py report.ncu-rep lib.so 'kernel-substring' [top]
+Needs the .so the report was captured from (built with -lineinfo).
+"""
+import csv, io, os, re, subprocess, sys, tempfile
+
+rep, so, pat = sys.argv[1], sys.argv[2], sys.argv[3]
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
+                     capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+kname = rows[0][1]
+hdr, data = rows[1], rows[2:]
+ix = {h: i for i, h in enumerate(hdr)}
+base = int(data[0][ix["Address"]], 16)
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
+line_of = {}
+for f in os.listdir(tmp):
+    if "dz_kernel.sm" not in f:
+        continue
+    txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+    cur_fn, cur_line, want = None, None, False
+    for ln in txt.splitlines():
+        m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
+        if m:
+            want = pat in m.group(1)
+            continue
+        if not want:
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+        if m:
+            cur_line = int(m.group(2))
+            continue
+        m = re.match(r"\s*/\*([0-9a-f]{4,6})\*/", ln)
+        if m:
+            line_of[int(m.group(1), 16)] = cur_line
+stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+agg = {}
+tot_s = tot_i = 0
+for r in data:
+    off = int(r[ix["Address"]], 16) - base
+    line = line_of.get(off)
+    a = agg.setdefault(line, dict(samples=0, instr=0, stalls={}))
+    s = int(r[ix["# Samples"]] or 0)
+    n = int(r[ix["Instructions Executed"]] or 0)
+    a["samples"] += s; a["instr"] += n
+    tot_s += s; tot_i += n
+    for h in stall_cols:
+        v = int(r[ix[h]] or 0)
+        if v:
+            a["stalls"][h] = a["stalls"].get(h, 0) + v
+src = open("/root/repo/dantzig_b200/csrc/dz_kernel.cu").read().splitlines()
+print(kname, "samples", tot_s, "warp-instr", tot_i)
+for line, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
+    st = sorted(a["stalls"].items(), key=lambda kv: -kv[1])[:3]
+    st = " ".join("%s=%.0f%%" % (k.replace("stall_", ""), 100 * v / max(a["samples"], 1)) for k, v in st)
+    text = src[line - 1].strip()[:70] if line and line <= len(src) else "?"
+    print("%5.1f%% smp %5.1f%% ins  L%-4s %-70s %s" % (100 * a["samples"] / tot_s, 100 * a["instr"] / tot_i, line, text, st))
