@@ -56,8 +56,8 @@ class TemplateInfo(C.Structure):
 class Options(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("max_pivots", C.c_int64), ("trace_cap", C.c_int32),
-        ("threads_per_row", C.c_int32), ("ctas_per_sm", C.c_int32), ("stream", C.c_void_p),
-        ("profile", C.c_int32),
+        ("worker_warps", C.c_int32), ("ctas_per_sm", C.c_int32), ("stream", C.c_void_p),
+        ("profile", C.c_int32), ("basis_home", C.c_int32),
     ]
 
 

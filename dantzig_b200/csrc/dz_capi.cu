@@ -239,8 +239,8 @@ int dz_batch_create(const dz_template *tc, int64_t B, const dz_options *opt, dz_
     rc = template_on_device(t, b->opt.device, &b->tview);
     if (rc != DZ_OK) return fail(rc);
     const dz::Template &h = t->host;
-    rc = dz::plan_launch(b->opt.device, h.m, h.n_int - h.m, B, b->opt.threads_per_row,
-                         b->opt.ctas_per_sm, &b->plan, &g_err);
+    rc = dz::plan_launch(b->opt.device, h.m, h.n_int - h.m, B, b->opt.worker_warps,
+                         b->opt.ctas_per_sm, b->opt.basis_home, &b->plan, &g_err);
     if (rc != DZ_OK) return fail(rc);
     if (b->opt.stream) {
         b->stream = (cudaStream_t)b->opt.stream;

@@ -72,8 +72,8 @@ struct LaunchPlan {
     int64_t gws_doubles_per_cta = 0;
 };
 
-int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t tpr_hint, int32_t cps_hint,
-                LaunchPlan *plan, std::string *err);
+int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t warps_hint, int32_t cps_hint,
+                int32_t basis_home, LaunchPlan *plan, std::string *err);
 // Enqueue the batched solve on `stream` (cudaStream_t passed as void*).
 int launch_batch(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan, void *stream,
                  std::string *err);

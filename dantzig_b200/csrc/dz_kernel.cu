@@ -33,11 +33,13 @@
 // When a back-substitution produces a non-finite value the skipping rules are
 // no longer no-ops (0*inf = NaN), so that solve is redone without skipping.
 //
-// THREAD MAP.  TPR*MP worker threads (MP = M rounded up to a warp): worker
-// (h, r) owns row r of W and the columns j == k+1+h (mod TPR) of the trailing
-// update, so an element is only ever written by the thread that reads it in the
-// next pivot search; plus one control warp that retires the virgin-unit steps,
-// keeps the position tables and runs the serial part of back-substitution.
+// THREAD MAP.  G worker warps + one control warp per CTA.  In the pivot search
+// and the multiplier computation worker threads stand for rows (column access,
+// odd row stride => conflict free); in the trailing update warps take rows of
+// the compact list of rows with a nonzero multiplier and lanes take columns
+// (row access, contiguous), four rows in flight per warp.  The control warp
+// retires the virgin-unit steps, keeps the position tables and runs the serial
+// part of back-substitution.  Two CTA barriers per non-trivial step.
 
 #include "dz_internal.h"
 
@@ -45,6 +47,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace dz {
 
@@ -55,7 +58,8 @@ constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ double load_ref(const double *__restrict__ th, int ref) {
     if (ref < 0) return 0.0;
-    const double v = __ldg(th + (ref >> 1));
+    // theta[0] is the constant 1.0 by contract (include/dantzig_b200.h): no load
+    const double v = (ref >> 1) == 0 ? 1.0 : __ldg(th + (ref >> 1));
     return (ref & 1) ? -v : v;
 }
 
@@ -124,12 +128,12 @@ __device__ __forceinline__ void block_argmax(Cand<N> &c, double *red_key, int *r
 
 struct Ctx {
     // problem
-    int M, Nn, S, MP, NW, nthreads, nwarps;
+    int M, Nn, S, NWK, G, nthreads, nwarps;
     // shared-memory arrays
     double *W;
-    double *x, *xb, *dxv, *vv, *z, *zb, *dzv;
+    double *x, *xb, *dxv, *vv, *z, *zb, *dzv, *lbuf;
     double *red_key;
-    int *bas, *nb, *rowAt, *posOf, *cnt, *unitRow, *retired, *pend, *red_idx, *ctl;
+    int *bas, *nb, *rowAt, *posOf, *cnt, *unitRow, *pend, *rlist, *pre, *red_idx, *ctl;
     int parity;
     // optional phase timing (thread 0 accumulates clock64 deltas into shared memory)
     long long *prof;
@@ -138,12 +142,13 @@ struct Ctx {
     unsigned long long n_lu, n_solve, n_price;
 };
 
-enum { CTL_K = 0, CTL_FLAG = 1, CTL_LP = 2 };
+enum { CTL_K = 0, CTL_FLAG = 1, CTL_LP = 2, CTL_NLIST = 3 };
 
 // Phase slots of the optional per-LP cycle profile (BatchDev::prof).
 enum {
     PH_STATUS = 0, PH_GATHER = 1, PH_ELIM = 2, PH_BACK_A = 3, PH_BACK_B = 4, PH_PRICE = 5,
-    PH_RATIO = 6, PH_UPDATE = 7, PH_NONTRIVIAL = 8, PH_PENDING = 9, PH_SOLVES = 10, PH_COUNT = 16
+    PH_RATIO = 6, PH_UPDATE = 7, PH_NONTRIVIAL = 8, PH_PENDING = 9, PH_SOLVES = 10,
+    PH_E_SEARCH = 11, PH_E_B2 = 12, PH_E_UPD = 13, PH_E_B1 = 14, PH_COUNT = 16
 };
 
 __device__ __forceinline__ void tick(Ctx &c, int slot) {
@@ -224,35 +229,34 @@ __device__ __forceinline__ int find_second(Ctx &c, double mu, const double *y, c
 // their own threads up front; the others run serially on the control warp with
 // exact-zero products skipped.  literal == true: every term, strictly serial.
 // Sets ctl[CTL_FLAG] when a non-finite value is produced.
-template <int TPR>
 __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal) {
     const int M = c.M, S = c.S, tid = threadIdx.x;
-    const bool worker = tid < c.NW;
-    const int r = tid % c.MP, h = tid / c.MP;
     double *W = c.W;
-    if (worker && h == 0 && r < M) {
-        const int i = c.posOf[r];
-        bool has_nz = literal;
-        if (!literal) {
-            const double *row = W + (size_t)r * S;
-            for (int j = i + 1; j < M; ++j)
-                if (row[j] != 0.0) {
-                    has_nz = true;
-                    break;
-                }
-        }
-        c.pend[i] = has_nz ? 1 : 0;
-        if (!has_nz) {
-            const double yi = __ddiv_rn(W[(size_t)r * S + M], W[(size_t)r * S + i]);
-            y[i] = yi;
-            if (!isfinite(yi)) c.ctl[CTL_FLAG] = 1;
-            c.n_solve += 1;
+    if (tid < c.NWK) {
+        for (int r = tid; r < M; r += c.NWK) {
+            const int i = c.posOf[r];
+            bool has_nz = literal;
+            if (!literal) {
+                const double *row = W + (size_t)r * S;
+                for (int j = i + 1; j < M; ++j)
+                    if (row[j] != 0.0) {
+                        has_nz = true;
+                        break;
+                    }
+            }
+            c.pend[i] = has_nz ? 1 : 0;
+            if (!has_nz) {
+                const double yi = __ddiv_rn(W[(size_t)r * S + M], W[(size_t)r * S + i]);
+                y[i] = yi;
+                if (!isfinite(yi)) c.ctl[CTL_FLAG] = 1;
+                c.n_solve += 1;
+            }
         }
     }
     __syncthreads();
     tick(c, PH_BACK_A);
-    if (!worker) { // control warp
-        const int lane = tid - c.NW;
+    if (tid >= c.NWK) { // control warp
+        const int lane = tid - c.NWK;
         for (int base = (M - 1) & ~31; base >= 0; base -= 32) {
             const int il = base + lane;
             unsigned pm = __ballot_sync(kFull, il < M && c.pend[il] != 0);
@@ -295,16 +299,15 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
 
 // lu_solve (linalg.rs:8-10) of B (transposed == false, rhs = column `arg` of A)
 // or of B^T (transposed == true, rhs = e_arg).  Result in y[0..M).
-template <int TPR>
 __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                                             const double *__restrict__ theta, bool transposed,
                                             int arg, double *y) {
     const int M = c.M, S = c.S, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     double *W = c.W;
-    const bool worker = tid < c.NW;
-    const int r = tid % c.MP, h = tid / c.MP;
 
     // ---- gather: W = dense(B) or dense(B^T), rhs in column M ----------------
+    // pre[p] = first flat entry of basis position p; position M is the rhs column.
     {
         const int total = M * S; // W is 16-byte aligned in both homes
         double2 *W2 = reinterpret_cast<double2 *>(W);
@@ -315,67 +318,100 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             c.unitRow[i] = -1;
             c.rowAt[i] = i;
             c.posOf[i] = i;
-            c.retired[i] = 0;
         }
         if (tid == 0) c.ctl[CTL_FLAG] = 0;
+        if (warp == c.nwarps - 1) { // exclusive scan of the column lengths (control warp)
+            const int per = (M + 1 + 31) >> 5;
+            const int b0 = lane * per;
+            int sum = 0;
+            for (int i = 0; i < per; ++i) {
+                const int p = b0 + i;
+                int len = 0;
+                if (p < M) {
+                    const int col = c.bas[p];
+                    len = T.col_ptr[col + 1] - T.col_ptr[col];
+                } else if (p == M && !transposed) {
+                    len = T.col_ptr[arg + 1] - T.col_ptr[arg];
+                }
+                sum += len;
+            }
+            int incl = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(kFull, incl, off);
+                if (lane >= off) incl += t;
+            }
+            int run = incl - sum;
+            for (int i = 0; i < per; ++i) {
+                const int p = b0 + i;
+                if (p <= M + 1) c.pre[p] = run;
+                int len = 0;
+                if (p < M) {
+                    const int col = c.bas[p];
+                    len = T.col_ptr[col + 1] - T.col_ptr[col];
+                } else if (p == M && !transposed) {
+                    len = T.col_ptr[arg + 1] - T.col_ptr[arg];
+                }
+                run += len;
+            }
+            if (lane == 31) c.pre[M + 1] = incl;
+        }
     }
     __syncthreads();
-    for (int p = tid; p < M; p += c.nthreads) {
-        const int col = c.bas[p];
-        const int e0 = T.col_ptr[col], e1 = T.col_ptr[col + 1];
-        int mycnt = 0, myrow = -1;
-        for (int e = e0; e < e1; ++e) {
+    {
+        const int total = c.pre[M + 1];
+        for (int idx = tid; idx < total; idx += c.nthreads) {
+            // largest p in [0, M] with pre[p] <= idx
+            int lo = 0, hi = M;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (c.pre[mid] <= idx)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            const int p = lo;
+            const int col = (p < M) ? c.bas[p] : arg;
+            const int e = T.col_ptr[col] + (idx - c.pre[p]);
             const double v = load_ref(theta, T.val_ref[e]);
             if (v != 0.0) {
                 const int row = T.row_idx[e];
-                if (!transposed) {
-                    W[(size_t)row * S + p] = v;
-                    ++mycnt;
-                    myrow = row;
+                if (p == M) {
+                    W[(size_t)row * S + M] = v;
                 } else {
-                    W[(size_t)p * S + row] = v;
-                    atomicAdd(&c.cnt[row], 1);
-                    c.unitRow[row] = p; // meaningful only where cnt ends at 1
+                    const int wr = transposed ? p : row, wc = transposed ? row : p;
+                    W[(size_t)wr * S + wc] = v;
+                    atomicAdd(&c.cnt[wc], 1);
+                    c.unitRow[wc] = wr; // meaningful only where cnt ends at 1
                 }
             }
         }
-        if (!transposed) {
-            c.cnt[p] = mycnt;
-            c.unitRow[p] = myrow;
-        }
-    }
-    if (!transposed) {
-        const int e0 = T.col_ptr[arg], e1 = T.col_ptr[arg + 1];
-        for (int e = e0 + tid; e < e1; e += c.nthreads) {
-            const double v = load_ref(theta, T.val_ref[e]);
-            if (v != 0.0) W[(size_t)T.row_idx[e] * S + M] = v;
-        }
-    } else if (tid == 0) {
-        W[(size_t)arg * S + M] = 1.0;
+        if (transposed && tid == 0) W[(size_t)arg * S + M] = 1.0;
     }
     __syncthreads();
     tick(c, PH_GATHER);
 
     // ---- elimination ---------------------------------------------------------
     int k = 0;
+    const bool is_ctl = (tid == c.NWK);
+    long long tb1 = (c.prof && tid == 0) ? clock64() : 0;
     for (;;) {
-        if (tid == c.NW) { // control thread: retire virgin-unit / empty columns
+        if (is_ctl) { // retire virgin-unit / empty columns: pure bookkeeping
             while (k < M - 1) {
                 const int cn = c.cnt[k];
                 if (cn == 0) { // all-zero column: mu = k, pivot 0, nothing moves (linalg.rs:117)
-                    c.retired[c.rowAt[k]] = 1;
                     ++k;
                     continue;
                 }
                 if (cn == 1) {
                     const int ur = c.unitRow[k];
-                    if (!c.retired[ur]) {
-                        const int mu = c.posOf[ur], rk = c.rowAt[k];
+                    const int mu = c.posOf[ur];
+                    if (mu >= k) { // its row is still active: no fill has reached this column
+                        const int rk = c.rowAt[k];
                         c.rowAt[k] = ur;
                         c.rowAt[mu] = rk;
                         c.posOf[ur] = k;
                         c.posOf[rk] = mu;
-                        c.retired[ur] = 1;
                         ++k;
                         continue;
                     }
@@ -383,85 +419,142 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                 break;
             }
             c.ctl[CTL_K] = k;
+            c.ctl[CTL_NLIST] = 0;
         }
-        __syncthreads();
+        __syncthreads(); // B1: updates of the previous step and the position tables are visible
         k = c.ctl[CTL_K];
+        long long tq = 0;
+        if (c.prof && tid == 0) {
+            tq = clock64();
+            c.prof[PH_E_B1] += tq - tb1;
+        }
         if (k >= M - 1) break;
 
-        // pivot search over the active rows of column k (linalg.rs:98-105)
-        Cand<1> cd;
-        cd.key[0] = 0.0;
-        cd.idx[0] = -1;
-        double v = 0.0;
-        bool active = false;
-        if (worker && r < M) {
-            const int myPos = c.posOf[r];
-            active = myPos >= k;
-            if (active) {
-                v = W[(size_t)r * S + k];
-                if (h == 0) {
-                    double key = fabs(v);
-                    if (v != v) key = (myPos == k) ? __longlong_as_double(0x7ff0000000000000LL) : -1.0;
-                    cd.key[0] = key;
-                    cd.idx[0] = (myPos << 16) | r;
-                }
+        // Pivot search over the active rows of column k (linalg.rs:98-105): largest
+        // |a_ik|, ties to the smallest logical position.  EVERY warp scans the whole
+        // column and reduces it with REDUX ops on the bit pattern of |v| (monotone for
+        // non-negative doubles), so no partial results cross warps.
+        unsigned bhi = 0u, blo = 0u;
+        int bidx = 0x7fffffff;
+        for (int r = lane; r < M; r += 32) {
+            const int pos = c.posOf[r];
+            if (pos < k) continue;
+            const double v = W[(size_t)r * S + k];
+            unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu, lo = (unsigned)__double2loint(v);
+            if (v != v) { // NaN never beats the incumbent, and is never beaten as incumbent
+                if (pos != k) continue;
+                hi = 0xffffffffu;
+                lo = 0xffffffffu;
+            }
+            const int packed = (pos << 16) | r;
+            if (bidx == 0x7fffffff || hi > bhi ||
+                (hi == bhi && (lo > blo || (lo == blo && packed < bidx)))) {
+                bhi = hi;
+                blo = lo;
+                bidx = packed;
             }
         }
-        block_argmax<1>(cd, c.red_key, c.red_idx, c.parity, c.MP >> 5);
-        const int pr = cd.idx[0] & 0xffff, ppos = cd.idx[0] >> 16;
+        const unsigned mh = __reduce_max_sync(kFull, bhi);
+        const unsigned ml = __reduce_max_sync(kFull, bhi == mh ? blo : 0u);
+        const int gi = __reduce_min_sync(kFull, (bhi == mh && blo == ml) ? bidx : 0x7fffffff);
+        const int pr = gi & 0xffff, ppos = gi >> 16;
         const double pv = W[(size_t)pr * S + k];
-        if (pv != 0.0 && worker) {
-            // rows with a zero multiplier are untouched (the pivot row is finite)
-            const bool need = active && r != pr && v != 0.0;
-            if (__any_sync(kFull, need)) {
-                const double l = need ? __ddiv_rn(v, pv) : 0.0;
-                const double *prow = W + (size_t)pr * S;
-                double *myrow = W + (size_t)r * S;
-                const int lane = tid & 31;
-                unsigned nupd = 0;
-                // the pivot row is read once per warp, 32 columns at a time; its nonzero
-                // columns are broadcast lane by lane (exact zeros of u are no-ops)
-                for (int c0 = k + 1 + 32 * h; c0 <= M; c0 += 32 * TPR) {
-                    const int jl = c0 + lane;
-                    const double ul = (jl <= M) ? prow[jl] : 0.0;
-                    unsigned mk = __ballot_sync(kFull, ul != 0.0);
-                    nupd += __popc(mk);
-                    while (mk) {
-                        const int b = __ffs(mk) - 1;
-                        mk &= mk - 1;
-                        const double u = __shfl_sync(kFull, ul, b);
-                        if (need) {
-                            const int j = c0 + b;
-                            myrow[j] = __dsub_rn(myrow[j], __dmul_rn(l, u));
-                        }
-                    }
-                }
-                if (need) c.n_lu += 2ull * nupd + (h == 0 ? 1 : 0);
-            }
+        if (c.prof && tid == 0) {
+            const long long t = clock64();
+            c.prof[PH_E_SEARCH] += t - tq;
+            tq = t;
         }
-        if (tid == c.NW) { // record the interchange k <-> ppos
+        __syncthreads(); // B2: every warp has read the positions it needs for this search
+        if (c.prof && tid == 0) {
+            const long long t = clock64();
+            c.prof[PH_E_B2] += t - tq;
+            tq = t;
+        }
+        if (is_ctl) { // record the interchange k <-> ppos (linalg.rs:107-114)
             if (c.prof) c.prof[PH_NONTRIVIAL] += 1;
             const int rk = c.rowAt[k];
             c.rowAt[k] = pr;
             c.rowAt[ppos] = rk;
             c.posOf[pr] = k;
             c.posOf[rk] = ppos;
-            c.retired[pr] = 1;
+        }
+        if (pv != 0.0 && warp < c.G) { // linalg.rs:117
+            // Worker warp w owns rows r = lane*G + w.  Multipliers l_i = a_ik / pivot live
+            // in registers; rows with an exact-zero entry are untouched by this step (the
+            // pivot row is finite).  Then lanes switch to columns: for every owned row
+            // with a multiplier, a_ij -= l_i * a_kj over the nonzero a_kj (linalg.rs:118-124),
+            // four rows in flight.
+            const int G = c.G;
+            const double *prow = W + (size_t)pr * S;
+            for (int rbase = 0; rbase * G < M; rbase += 32) {
+                const int r_own = (rbase + lane) * G + warp;
+                bool need = false;
+                double l = 0.0;
+                if (r_own < M && r_own != pr && c.posOf[r_own] >= k) {
+                    const double v = W[(size_t)r_own * S + k];
+                    if (v != 0.0) {
+                        need = true;
+                        l = __ddiv_rn(v, pv);
+                    }
+                }
+                unsigned rows = __ballot_sync(kFull, need);
+                unsigned long long upd = 0;
+                while (rows) {
+                    // peel up to four rows
+                    const int b0 = __ffs(rows) - 1;
+                    rows &= rows - 1;
+                    const int b1 = rows ? __ffs(rows) - 1 : -1;
+                    if (rows) rows &= rows - 1;
+                    const int b2 = rows ? __ffs(rows) - 1 : -1;
+                    if (rows) rows &= rows - 1;
+                    const int b3 = rows ? __ffs(rows) - 1 : -1;
+                    if (rows) rows &= rows - 1;
+                    const double l0 = __shfl_sync(kFull, l, b0);
+                    const double l1 = __shfl_sync(kFull, l, b1 < 0 ? 0 : b1);
+                    const double l2 = __shfl_sync(kFull, l, b2 < 0 ? 0 : b2);
+                    const double l3 = __shfl_sync(kFull, l, b3 < 0 ? 0 : b3);
+                    double *w0 = W + (size_t)((rbase + b0) * G + warp) * S;
+                    double *w1 = W + (size_t)((rbase + (b1 < 0 ? b0 : b1)) * G + warp) * S;
+                    double *w2 = W + (size_t)((rbase + (b2 < 0 ? b0 : b2)) * G + warp) * S;
+                    double *w3 = W + (size_t)((rbase + (b3 < 0 ? b0 : b3)) * G + warp) * S;
+                    for (int c0 = k + 1; c0 <= M; c0 += 32) {
+                        const int j = c0 + lane;
+                        const double u = (j <= M) ? prow[j] : 0.0;
+                        if (u != 0.0) {
+                            const double a0 = w0[j];
+                            const double a1 = (b1 >= 0) ? w1[j] : 0.0;
+                            const double a2 = (b2 >= 0) ? w2[j] : 0.0;
+                            const double a3 = (b3 >= 0) ? w3[j] : 0.0;
+                            w0[j] = __dsub_rn(a0, __dmul_rn(l0, u));
+                            if (b1 >= 0) w1[j] = __dsub_rn(a1, __dmul_rn(l1, u));
+                            if (b2 >= 0) w2[j] = __dsub_rn(a2, __dmul_rn(l2, u));
+                            if (b3 >= 0) w3[j] = __dsub_rn(a3, __dmul_rn(l3, u));
+                            upd += 1 + (b1 >= 0) + (b2 >= 0) + (b3 >= 0);
+                        }
+                    }
+                }
+                c.n_lu += 2ull * upd + (need ? 1 : 0);
+            }
+        }
+        if (c.prof && tid == 0) {
+            tb1 = clock64();
+            c.prof[PH_E_UPD] += tb1 - tq;
         }
         ++k;
     }
     tick(c, PH_ELIM);
     if (c.prof && tid == 0) c.prof[PH_SOLVES] += 1;
     // ---- back substitution ------------------------------------------------------
-    back_substitute<TPR>(c, y, false);
-    if (c.ctl[CTL_FLAG]) {
+    // (second trip only when a non-finite value appeared: redo without skipping)
+    for (int literal = 0; literal < 2; ++literal) {
+        back_substitute(c, y, literal != 0);
+        if (literal || !c.ctl[CTL_FLAG]) break;
         __syncthreads();
         if (tid == 0) c.ctl[CTL_FLAG] = 0;
-        back_substitute<TPR>(c, y, true);
     }
 }
 
-template <int TPR, bool WSMEM>
+template <bool WSMEM>
 __global__ void __launch_bounds__(1024, 1)
 dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -469,17 +562,17 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
     c.M = T.M;
     c.Nn = T.Nn;
     c.S = (T.M + 1) | 1;
-    c.MP = (T.M + 31) & ~31;
-    c.NW = TPR * c.MP;
     c.nthreads = blockDim.x;
     c.nwarps = blockDim.x >> 5;
+    c.G = c.nwarps - 1;
+    c.NWK = c.G * 32;
     c.parity = 0;
     const int M = c.M, Nn = c.Nn, tid = threadIdx.x;
     {
         double *dp = reinterpret_cast<double *>(smem_raw);
         if (WSMEM) {
             c.W = dp;
-            dp += (size_t)M * c.S;
+            dp += ((size_t)M * c.S + 1) & ~(size_t)1;
         } else {
             c.W = Bt.gws + (size_t)blockIdx.x * Bt.gws_stride;
         }
@@ -487,6 +580,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
         c.xb = dp, dp += M;
         c.dxv = dp, dp += M;
         c.vv = dp, dp += M;
+        c.lbuf = dp, dp += M;
         c.z = dp, dp += Nn;
         c.zb = dp, dp += Nn;
         c.dzv = dp, dp += Nn;
@@ -500,8 +594,9 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
         c.posOf = ip, ip += M;
         c.cnt = ip, ip += M;
         c.unitRow = ip, ip += M;
-        c.retired = ip, ip += M;
         c.pend = ip, ip += M;
+        c.rlist = ip, ip += M;
+        c.pre = ip, ip += M + 2;
         c.red_idx = ip, ip += 2 * 4 * kMaxWarps;
         c.ctl = ip, ip += 8;
     }
@@ -572,46 +667,56 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
                 status = DZ_PIVOT_CAP;
                 break;
             }
-            int p, q;
-            if (primal_step) { // simplex.rs:308-318
-                q = q0;
-                basis_solve<TPR>(c, T, theta, false, c.nb[q], c.dxv);
-                p = find_second(c, mu, c.x, c.xb, c.dxv, M);
-                tick(c, PH_RATIO);
-                if (p < 0) {
-                    status = DZ_UNBOUNDED;
-                    break;
-                }
-                basis_solve<TPR>(c, T, theta, true, p, c.vv);
-            } else { // simplex.rs:320-330
-                p = p0;
-                basis_solve<TPR>(c, T, theta, true, p, c.vv);
-            }
-            // pricing: dz = -N^T v (simplex.rs:235, linalg.rs:199-207)
-            for (int k = tid; k < Nn; k += c.nthreads) {
-                const int col = c.nb[k];
-                const int e0 = T.col_ptr[col], e1 = T.col_ptr[col + 1];
-                double s = 0.0;
-                for (int e = e0; e < e1; ++e) {
-                    const double a = load_ref(theta, T.val_ref[e]);
-                    if (a != 0.0) {
-                        s = __dadd_rn(s, __dmul_rn(a, -c.vv[T.row_idx[e]]));
-                        c.n_price += 2;
+            // primal_step (simplex.rs:308-318): dx = B^-1 a_j, ratio test on x, then dz;
+            // dual_step   (simplex.rs:320-330): dz first, ratio test on z, then dx.
+            // One solve call site serves both orders.
+            int p = p0, q = q0;
+            bool failed = false;
+            for (int pass = 0; pass < 2; ++pass) {
+                const bool transposed = (pass == 0) != primal_step;
+                basis_solve(c, T, theta, transposed, transposed ? p : c.nb[q],
+                            transposed ? c.vv : c.dxv);
+                if (transposed) {
+                    // pricing: dz = -N^T v (simplex.rs:235, linalg.rs:199-207); each
+                    // column is summed sequentially in ascending row order
+                    for (int k = tid; k < Nn; k += c.nthreads) {
+                        const int col = c.nb[k];
+                        const int e0 = T.col_ptr[col], e1 = T.col_ptr[col + 1];
+                        double s = 0.0;
+                        unsigned cntp = 0;
+#pragma unroll 4
+                        for (int e = e0; e < e1; ++e) {
+                            const double a = load_ref(theta, T.val_ref[e]);
+                            const double t = __dadd_rn(s, __dmul_rn(a, -c.vv[T.row_idx[e]]));
+                            const bool nz = (a != 0.0);
+                            s = nz ? t : s;
+                            cntp += nz ? 2u : 0u;
+                        }
+                        c.n_price += cntp;
+                        c.dzv[k] = s;
                     }
+                    __syncthreads();
+                    tick(c, PH_PRICE);
                 }
-                c.dzv[k] = s;
-            }
-            __syncthreads();
-            tick(c, PH_PRICE);
-            if (!primal_step) {
-                q = find_second(c, mu, c.z, c.zb, c.dzv, Nn);
-                tick(c, PH_RATIO);
-                if (q < 0) {
-                    status = DZ_INFEASIBLE;
-                    break;
+                if (pass == 0) {
+                    if (primal_step) {
+                        p = find_second(c, mu, c.x, c.xb, c.dxv, M);
+                        if (p < 0) {
+                            status = DZ_UNBOUNDED;
+                            failed = true;
+                        }
+                    } else {
+                        q = find_second(c, mu, c.z, c.zb, c.dzv, Nn);
+                        if (q < 0) {
+                            status = DZ_INFEASIBLE;
+                            failed = true;
+                        }
+                    }
+                    tick(c, PH_RATIO);
+                    if (failed) break;
                 }
-                basis_solve<TPR>(c, T, theta, false, c.nb[q], c.dxv);
             }
+            if (failed) break;
             // ---- Simplex::pivot, simplex.rs:253-268 ----
             const int leaving = c.bas[p], entering = c.nb[q];
             double t, s, t_bar, s_bar;
@@ -691,8 +796,6 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
         if (Bt.basis)
             for (int p = tid; p < M; p += c.nthreads) Bt.basis[(size_t)lp * M + p] = c.bas[p];
         if (Bt.values) {
-            // position of each basic column, reusing posOf as scratch over columns is not
-            // possible (n_int > M), so search: n_orig*M/threads compares, once per LP.
             for (int v = tid; v < T.n_orig; v += c.nthreads) {
                 const int cp = T.pos_index[v], cn = T.neg_index[v];
                 double pos = 0.0, neg = 0.0;
@@ -721,16 +824,16 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
 
 size_t smem_bytes_for(int M, int Nn, bool w_in_smem) {
     const size_t S = (size_t)((M + 1) | 1);
-    size_t doubles = (w_in_smem ? (size_t)M * S : 0) + 4 * (size_t)M + 3 * (size_t)Nn +
-                     2 * 4 * kMaxWarps + PH_COUNT;
-    size_t ints = 7 * (size_t)M + (size_t)Nn + 2 * 4 * kMaxWarps + 8;
+    size_t doubles = (w_in_smem ? (((size_t)M * S + 1) & ~(size_t)1) : 0) + 5 * (size_t)M +
+                     3 * (size_t)Nn + 2 * 4 * kMaxWarps + PH_COUNT;
+    size_t ints = 8 * (size_t)M + 2 + (size_t)Nn + 2 * 4 * kMaxWarps + 8;
     return doubles * 8 + ints * 4 + 16;
 }
 
-template <int TPR, bool WS>
+template <bool WS>
 cudaError_t launch_one(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan,
                        cudaStream_t st) {
-    auto kern = dz_batch_kernel<TPR, WS>;
+    auto kern = dz_batch_kernel<WS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          plan.smem_bytes);
     if (e != cudaSuccess) return e;
@@ -740,51 +843,61 @@ cudaError_t launch_one(const TemplateDev &T, const BatchDev &Bt, const LaunchPla
 
 } // namespace
 
-int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t tpr_hint, int32_t cps_hint,
-                LaunchPlan *plan, std::string *err) {
+int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t warps_hint, int32_t cps_hint,
+                int32_t basis_home, LaunchPlan *plan, std::string *err) {
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) {
         *err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
         return DZ_ERR_CUDA;
     }
-    if (M >= 65535) {
-        *err = "batched kernel supports m_int < 65535";
-        return DZ_ERR_LIMIT;
-    }
-    const int MP = std::max(32, (M + 31) & ~31);
-    int tpr = tpr_hint > 0 ? tpr_hint : 1;
-    while (tpr > 1 && tpr * MP + 32 > 1024) tpr >>= 1;
-    if (tpr != 1 && tpr != 2 && tpr != 4) tpr = 1;
-    if (MP + 32 > 1024) {
-        *err = "batched kernel supports m_int <= 992 (one worker thread per basis row)";
+    if (M >= 32768) {
+        *err = "batched kernel supports m_int < 32768";
         return DZ_ERR_LIMIT;
     }
     const size_t max_smem = prop.sharedMemPerBlockOptin;
     const size_t per_sm = prop.sharedMemPerMultiprocessor;
     const size_t with_w = smem_bytes_for(M, Nn, true);
-    plan->tpr = tpr;
-    plan->block = tpr * MP + 32;
-    if (with_w <= max_smem) {
-        plan->w_in_smem = true;
-        plan->smem_bytes = (int32_t)with_w;
-        plan->gws_doubles_per_cta = 0;
-    } else {
-        plan->w_in_smem = false;
-        const size_t without = smem_bytes_for(M, Nn, false);
-        if (without > max_smem) {
-            *err = "problem too large for the batched kernel's shared-memory state";
-            return DZ_ERR_LIMIT;
-        }
-        plan->smem_bytes = (int32_t)without;
-        plan->gws_doubles_per_cta = (int64_t)M * ((M + 1) | 1);
+    const size_t without = smem_bytes_for(M, Nn, false);
+    if (without > max_smem) {
+        *err = "problem too large for the batched kernel's shared-memory state";
+        return DZ_ERR_LIMIT;
     }
+    const int sms = prop.multiProcessorCount;
+    // Where the dense working basis lives.  The kernel is bound by dependent-issue
+    // latency, so LPs in flight per SM is what buys throughput: with the basis in
+    // shared memory only floor(227 KB / (8 M^2)) CTAs fit per SM; with it in an
+    // HBM workspace (L2 resident: grid * 8 M^2 bytes) up to 12 do.  Measured on
+    // config 2 (profiles/): 3.3 kLP/s shared vs 5.1 kLP/s workspace.  Small batches
+    // (fewer LPs than the shared-memory grid) keep the lower-latency shared home.
+    const int cps_smem = with_w <= max_smem ? (int)(per_sm / (with_w + 1024)) : 0;
+    bool in_smem;
+    if (basis_home == 1)
+        in_smem = cps_smem > 0;
+    else if (basis_home == 2)
+        in_smem = false;
+    else
+        in_smem = cps_smem > 0 && (cps_smem >= 6 || B <= (int64_t)sms * cps_smem);
+    int g = warps_hint > 0 ? warps_hint
+                           : (in_smem ? std::min(8, std::max(2, (M + 31) / 32 + 1))
+                                      : std::min(8, std::max(2, (M + 31) / 32)));
+    g = std::max(1, std::min(g, 31));
+    plan->tpr = g;
+    plan->block = (g + 1) * 32;
+    plan->w_in_smem = in_smem;
+    plan->smem_bytes = (int32_t)(in_smem ? with_w : without);
+    plan->gws_doubles_per_cta = in_smem ? 0 : (((int64_t)M * ((M + 1) | 1) + 1) & ~(int64_t)1);
     int cps = (int)(per_sm / ((size_t)plan->smem_bytes + 1024));
     cps = std::max(1, std::min(cps, 2048 / plan->block));
-    cps = std::min(cps, 32);
+    cps = std::min(cps, in_smem ? 32 : 12);
+    if (!in_smem) { // keep the workspace L2 resident
+        const double ws_bytes = 8.0 * (double)plan->gws_doubles_per_cta;
+        const int fit = (int)(0.75 * (double)prop.l2CacheSize / (ws_bytes * sms));
+        cps = std::max(1, std::min(cps, std::max(fit, 1)));
+    }
     if (cps_hint > 0) cps = std::min(cps, cps_hint);
     plan->ctas_per_sm = cps;
-    int64_t grid = (int64_t)prop.multiProcessorCount * cps;
+    int64_t grid = (int64_t)sms * cps;
     if (grid > B) grid = B;
     if (grid < 1) grid = 1;
     plan->grid = (int32_t)grid;
@@ -795,15 +908,7 @@ int launch_batch(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &pla
                  std::string *err) {
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
-#define DZ_LAUNCH(TPR)                                                                            \
-    e = plan.w_in_smem ? launch_one<TPR, true>(T, Bt, plan, st)                                   \
-                       : launch_one<TPR, false>(T, Bt, plan, st)
-    switch (plan.tpr) {
-    case 4: DZ_LAUNCH(4); break;
-    case 2: DZ_LAUNCH(2); break;
-    default: DZ_LAUNCH(1); break;
-    }
-#undef DZ_LAUNCH
+    e = plan.w_in_smem ? launch_one<true>(T, Bt, plan, st) : launch_one<false>(T, Bt, plan, st);
     if (e != cudaSuccess) {
         *err = std::string("dz_batch_kernel launch: ") + cudaGetErrorString(e);
         return DZ_ERR_CUDA;

@@ -96,12 +96,13 @@ class BatchResult:
     prof: np.ndarray | None = None  # [B, 16] phase cycles (profile=True)
 
 
-def _options(device=0, max_pivots=0, trace_cap=0, threads_per_row=0, ctas_per_sm=0, stream=None,
-             profile=False):
+def _options(device=0, max_pivots=0, trace_cap=0, worker_warps=0, ctas_per_sm=0, stream=None,
+             profile=False, basis_home=0):
     o = _capi.Options()
     _capi.lib().dz_options_default(C.byref(o))
     o.device, o.max_pivots, o.trace_cap = int(device), int(max_pivots), int(trace_cap)
-    o.threads_per_row, o.ctas_per_sm = int(threads_per_row), int(ctas_per_sm)
+    o.worker_warps, o.ctas_per_sm = int(worker_warps), int(ctas_per_sm)
+    o.basis_home = int(basis_home)
     o.stream = stream
     o.profile = 1 if profile else 0
     return o
@@ -111,12 +112,14 @@ class Batch:
     """B LPs sharing one template, resident on one GPU."""
 
     def __init__(self, template: Template, B: int, *, device: int = 0, max_pivots: int = 0,
-                 trace_cap: int = 0, threads_per_row: int = 0, ctas_per_sm: int = 0,
-                 stream: int | None = None, want_basis: bool = False, profile: bool = False):
+                 trace_cap: int = 0, worker_warps: int = 0, ctas_per_sm: int = 0,
+                 stream: int | None = None, want_basis: bool = False, profile: bool = False,
+                 basis_home: int = 0):
         self.template, self.B = template, int(B)
         self.trace_cap, self.want_basis, self.profile = int(trace_cap), want_basis, profile
         self._h = C.c_void_p()
-        o = _options(device, max_pivots, trace_cap, threads_per_row, ctas_per_sm, stream, profile)
+        o = _options(device, max_pivots, trace_cap, worker_warps, ctas_per_sm,
+                     stream, profile, basis_home)
         _capi.check(_capi.lib().dz_batch_create(template.handle, self.B, C.byref(o),
                                                 C.byref(self._h)))
 

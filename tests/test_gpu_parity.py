@@ -86,11 +86,13 @@ def _check_batch(oracle, w, res, n_oracle, variant):
 
 
 @pytest.mark.parametrize("wl", sorted(cases.GOLDEN_WORKLOADS))
-@pytest.mark.parametrize("tpr", [0, 2])
-def test_batch_parity(oracle, wl, tpr):
+@pytest.mark.parametrize("shape", [(0, 0), (1, 2), (3, 1)], ids=["auto", "1warp-hbm", "3warps-smem"])
+def test_batch_parity(oracle, wl, shape):
+    """Every launch shape (worker warps per LP, home of the working basis) must
+    give the same bits: they only change which thread does which operation."""
     w = cases.GOLDEN_WORKLOADS[wl]()
     t = Template(w.structure)
-    res = solve_batch(t, w.theta, trace_cap=256, threads_per_row=tpr)
+    res = solve_batch(t, w.theta, trace_cap=256, worker_warps=shape[0], basis_home=shape[1])
     g = json.load(open(os.path.join(GOLD, wl + ".json")))
     assert sha(w.theta) == g["theta_sha"]
     for i, e in enumerate(g["lps"]):                             # every LP against the fixture
@@ -132,7 +134,7 @@ def test_full_config2_properties(oracle):
     w = generate.config2(4096)
     t = Template(w.structure)
     r = solve_batch(t, w.theta)
-    r2 = solve_batch(t, w.theta, threads_per_row=4, ctas_per_sm=1)
+    r2 = solve_batch(t, w.theta, worker_warps=4, ctas_per_sm=1, basis_home=1)
     assert np.array_equal(r.trace_hash, r2.trace_hash) and np.array_equal(r.objective, r2.objective)
     assert sorted(np.flatnonzero(r.status != 0).tolist()) == [287, 2142, 3300]
     assert (r.status[[287, 2142, 3300]] == 1).all()

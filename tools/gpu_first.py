@@ -34,12 +34,12 @@ bad += parity(generate.small_batch(64, 8, 16), 64)
 bad += parity(generate.mixed_batch(64, 9, 12), 64)
 bad += parity(generate.config2(64), 64)
 for tpr in (1, 2, 4):
-    bad += parity(generate.config2(64), 16, threads_per_row=tpr)
+    bad += parity(generate.config2(64), 16, worker_warps=tpr)
 w = generate.config2(4096)
 t = Template(w.structure)
 for tpr in (1, 2, 4):
     for cps in (1, 2):
-        b = Batch(t, w.B, threads_per_row=tpr, ctas_per_sm=cps)
+        b = Batch(t, w.B, worker_warps=tpr, ctas_per_sm=cps)
         b.upload(w.theta)
         for rep in range(2):
             b.solve(); b.sync()

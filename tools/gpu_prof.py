@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from dantzig_b200 import generate, Template, Batch
 names = ["status","gather","elim","back_a","back_b","price","ratio","update","#nontriv","#pending","#solves"]
+sub = ["e_search","e_b2wait","e_div+upd","e_b1wait"]
 def run(w, **kw):
     t = Template(w.structure)
     b = Batch(t, w.B, profile=True, **kw)
@@ -18,10 +19,12 @@ def run(w, **kw):
             print("  %-9s %10.0f cyc/pivot  %5.1f%%" % (n, p[:, i].sum()/piv, 100*p[:, i].sum()/tot))
         else:
             print("  %-9s %10.2f per solve" % (n, p[:, i].sum()/max(p[:, 10].sum(),1)))
+    for i, n in enumerate(sub):
+        print("  %-9s %10.0f cyc per nontrivial step" % (n, p[:, 11+i].sum()/max(p[:,8].sum(),1)))
     print("  total cyc/pivot %.0f ; cyc per nontrivial step %.0f ; cyc per pending row %.0f" % (tot/piv, p[:,2].sum()/max(p[:,8].sum(),1), p[:,4].sum()/max(p[:,9].sum(),1)))
     b.close()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 w = generate.config2(B)
-for tpr in (1, 4):
-    run(w, threads_per_row=tpr)
-run(w, threads_per_row=4, ctas_per_sm=1)
+for tpr in (4, 8):
+    run(w, worker_warps=tpr)
+run(w, worker_warps=4, ctas_per_sm=1)
