@@ -183,7 +183,10 @@ def run_gpu(args) -> None:
     dev = torch.device("cuda", local)
 
     # this rank's shard: LP ids [rank*B, (rank+1)*B) of the config-2 family
-    w = generate.config2(B_PER_GPU, first=rank * B_PER_GPU)
+    from dantzig_b200.sharding import shard_range
+
+    lo, hi = shard_range(world * B_PER_GPU, rank, world)
+    w = generate.config2(hi - lo, first=lo)
     tmpl = Template(w.structure)
     batch = Batch(tmpl, w.B, device=local)
     pinned = torch.empty(w.theta.shape, dtype=torch.float64).pin_memory()
@@ -242,16 +245,11 @@ def run_gpu(args) -> None:
                                  res_e2e.work))
 
     # ---- the one collective: final gather of per-LP results ------------------------
-    status = torch.from_numpy(res.status.astype(np.int32)).to(dev)
-    obj = torch.from_numpy(res.objective).to(dev)
-    if dist is not None:
-        gs = [torch.empty_like(status) for _ in range(world)]
-        go = [torch.empty_like(obj) for _ in range(world)]
-        dist.all_gather(gs, status)
-        dist.all_gather(go, obj)
-        status_all = torch.cat(gs).cpu().numpy()
-    else:
-        status_all = res.status
+    from dantzig_b200.sharding import gather_results
+
+    full = gather_results({"status": res.status, "objective": res.objective, "pivots": res.pivots},
+                          world * w.B, dist, dev)
+    status_all = full["status"]
     clocks = sampler.stop(c0, c1) if sampler else None
 
     if rank == 0:

@@ -890,12 +890,7 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t warps_hint
     int cps = (int)(per_sm / ((size_t)plan->smem_bytes + 1024));
     cps = std::max(1, std::min(cps, 2048 / plan->block));
     cps = std::min(cps, in_smem ? 32 : 12);
-    if (!in_smem) { // keep the workspace L2 resident
-        const double ws_bytes = 8.0 * (double)plan->gws_doubles_per_cta;
-        const int fit = (int)(0.75 * (double)prop.l2CacheSize / (ws_bytes * sms));
-        cps = std::max(1, std::min(cps, std::max(fit, 1)));
-    }
-    if (cps_hint > 0) cps = std::min(cps, cps_hint);
+    if (cps_hint > 0) cps = std::min(std::max(1, std::min((int)(per_sm / ((size_t)plan->smem_bytes + 1024)), 2048 / plan->block)), cps_hint);
     plan->ctas_per_sm = cps;
     int64_t grid = (int64_t)sms * cps;
     if (grid > B) grid = B;

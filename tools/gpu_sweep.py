@@ -1,0 +1,16 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from dantzig_b200 import generate, Template, Batch
+def run(w, **kw):
+    t = Template(w.structure)
+    b = Batch(t, w.B, **kw)
+    b.upload(w.theta); b.solve(); b.sync()
+    r = b.download(light=True)
+    ms = b.kernel_ms()
+    print(w.name, "B", w.B, kw, b.launch_info(), "ms %.1f" % ms, "LP/s %.1f" % (w.B/ms*1e3), "pivots/s %.0f" % (r.pivots.sum()/ms*1e3), flush=True)
+    b.close()
+w5 = generate.config5(2368)
+for G, cps in ((6, 4), (6, 8), (4, 8), (4, 12), (8, 6)):
+    run(w5, worker_warps=G, ctas_per_sm=cps)
+run(w5)
