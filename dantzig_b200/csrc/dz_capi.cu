@@ -283,7 +283,7 @@ int dz_batch_create(const dz_template *tc, int64_t B, const dz_options *opt, dz_
         return fail(DZ_ERR_ALLOC);
     }
     if (b->plan.gws_doubles_per_cta > 0) {
-        const size_t bytes = sizeof(double) * (size_t)b->plan.gws_doubles_per_cta * b->plan.grid;
+        const size_t bytes = sizeof(double) * (size_t)b->plan.gws_doubles_per_cta * (size_t)b->plan.teams;
         if (cudaMalloc(&b->d_gws, bytes) != cudaSuccess) {
             g_err = "cudaMalloc failed for the basis workspace";
             cudaGetLastError();

@@ -81,8 +81,8 @@ template <int N> struct Cand {
 // for the result.
 template <int N>
 __device__ __forceinline__ void block_argmax(Cand<N> &c, double *red_key, int *red_idx,
-                                             int &parity, int nparts) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                                             int &parity, int nparts, int tid, bool wm) {
+    const int warp = tid >> 5, lane = tid & 31;
     const int nwarps = nparts;
     if (warp < nparts) {
 #pragma unroll
@@ -98,6 +98,7 @@ __device__ __forceinline__ void block_argmax(Cand<N> &c, double *red_key, int *r
             }
         }
     }
+    if (wm) return; // single warp: the butterfly left the result in every lane
     double *rk = red_key + (size_t)parity * N * kMaxWarps;
     int *ri = red_idx + (size_t)parity * N * kMaxWarps;
     if (lane == 0 && warp < nparts) {
@@ -129,11 +130,13 @@ __device__ __forceinline__ void block_argmax(Cand<N> &c, double *red_key, int *r
 struct Ctx {
     // problem
     int M, Nn, S, NWK, G, nthreads, nwarps;
+    int tid;  // thread index within the team that solves one LP (CTA, or a single warp)
+    bool wm;  // warp mode: one warp per LP, team barrier = __syncwarp
     // shared-memory arrays
     double *W;
-    double *x, *xb, *dxv, *vv, *z, *zb, *dzv, *lbuf;
+    double *x, *xb, *dxv, *vv, *z, *zb, *dzv;
     double *red_key;
-    int *bas, *nb, *rowAt, *posOf, *cnt, *unitRow, *pend, *rlist, *pre, *red_idx, *ctl;
+    int *bas, *nb, *rowAt, *posOf, *cnt, *unitRow, *pend, *pre, *red_idx, *ctl;
     int parity;
     // optional phase timing (thread 0 accumulates clock64 deltas into shared memory)
     long long *prof;
@@ -151,8 +154,16 @@ enum {
     PH_E_SEARCH = 11, PH_E_B2 = 12, PH_E_UPD = 13, PH_E_B1 = 14, PH_COUNT = 16
 };
 
+// Team barrier: the CTA in CTA-per-LP mode, the warp in warp-per-LP mode.
+__device__ __forceinline__ void csync(const Ctx &c) {
+    if (c.wm)
+        __syncwarp();
+    else
+        __syncthreads();
+}
+
 __device__ __forceinline__ void tick(Ctx &c, int slot) {
-    if (c.prof && threadIdx.x == 0) {
+    if (c.prof && c.tid == 0) {
         const long long now = clock64();
         c.prof[slot] += now - c.t_last;
         c.t_last = now;
@@ -170,7 +181,7 @@ __device__ __forceinline__ void find_first_both(Ctx &c, int &q0, int &p0) {
         cd.key[n] = 0.0;
         cd.idx[n] = -1;
     }
-    for (int k = threadIdx.x; k < c.Nn; k += c.nthreads) {
+    for (int k = c.tid; k < c.Nn; k += c.nthreads) {
         const double yb = c.zb[k];
         if (yb > 0.0) {
             const double ratio = __ddiv_rn(-c.z[k], yb);
@@ -181,7 +192,7 @@ __device__ __forceinline__ void find_first_both(Ctx &c, int &q0, int &p0) {
             if (cd.idx[1] < 0) cd.idx[1] = k; // k ascends per thread
         }
     }
-    for (int k = threadIdx.x; k < c.M; k += c.nthreads) {
+    for (int k = c.tid; k < c.M; k += c.nthreads) {
         const double yb = c.xb[k];
         if (yb > 0.0) {
             const double ratio = __ddiv_rn(-c.x[k], yb);
@@ -192,7 +203,7 @@ __device__ __forceinline__ void find_first_both(Ctx &c, int &q0, int &p0) {
             if (cd.idx[3] < 0) cd.idx[3] = k;
         }
     }
-    block_argmax<4>(cd, c.red_key, c.red_idx, c.parity, c.nwarps);
+    block_argmax<4>(cd, c.red_key, c.red_idx, c.parity, c.nwarps, c.tid, c.wm);
     q0 = cd.idx[0];
     if (cd.idx[1] >= 0) {
         const double r = __ddiv_rn(-c.z[cd.idx[1]], c.zb[cd.idx[1]]);
@@ -212,7 +223,7 @@ __device__ __forceinline__ int find_second(Ctx &c, double mu, const double *y, c
     Cand<1> cd;
     cd.key[0] = 0.0;
     cd.idx[0] = -1;
-    for (int k = threadIdx.x; k < len; k += c.nthreads) {
+    for (int k = c.tid; k < len; k += c.nthreads) {
         const double denom = __dadd_rn(y[k], __dmul_rn(mu, yb[k]));
         const double ratio = __ddiv_rn(dy[k], denom);
         if (ratio > 0.0 && beats(ratio, k, cd.key[0], cd.idx[0])) {
@@ -220,7 +231,7 @@ __device__ __forceinline__ int find_second(Ctx &c, double mu, const double *y, c
             cd.idx[0] = k;
         }
     }
-    block_argmax<1>(cd, c.red_key, c.red_idx, c.parity, c.nwarps);
+    block_argmax<1>(cd, c.red_key, c.red_idx, c.parity, c.nwarps, c.tid, c.wm);
     return cd.idx[0];
 }
 
@@ -230,7 +241,7 @@ __device__ __forceinline__ int find_second(Ctx &c, double mu, const double *y, c
 // exact-zero products skipped.  literal == true: every term, strictly serial.
 // Sets ctl[CTL_FLAG] when a non-finite value is produced.
 __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal) {
-    const int M = c.M, S = c.S, tid = threadIdx.x;
+    const int M = c.M, S = c.S, tid = c.tid;
     double *W = c.W;
     if (tid < c.NWK) {
         for (int r = tid; r < M; r += c.NWK) {
@@ -253,10 +264,10 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
             }
         }
     }
-    __syncthreads();
+    csync(c);
     tick(c, PH_BACK_A);
-    if (tid >= c.NWK) { // control warp
-        const int lane = tid - c.NWK;
+    if (c.wm || tid >= c.NWK) { // control warp (the warp itself in warp mode)
+        const int lane = c.wm ? tid : tid - c.NWK;
         for (int base = (M - 1) & ~31; base >= 0; base -= 32) {
             const int il = base + lane;
             unsigned pm = __ballot_sync(kFull, il < M && c.pend[il] != 0);
@@ -293,7 +304,7 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
             }
         }
     }
-    __syncthreads();
+    csync(c);
     tick(c, PH_BACK_B);
 }
 
@@ -302,7 +313,7 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
 __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                                             const double *__restrict__ theta, bool transposed,
                                             int arg, double *y) {
-    const int M = c.M, S = c.S, tid = threadIdx.x;
+    const int M = c.M, S = c.S, tid = c.tid;
     const int lane = tid & 31, warp = tid >> 5;
     double *W = c.W;
 
@@ -357,7 +368,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             if (lane == 31) c.pre[M + 1] = incl;
         }
     }
-    __syncthreads();
+    csync(c);
     {
         const int total = c.pre[M + 1];
         for (int idx = tid; idx < total; idx += c.nthreads) {
@@ -388,12 +399,12 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
         }
         if (transposed && tid == 0) W[(size_t)arg * S + M] = 1.0;
     }
-    __syncthreads();
+    csync(c);
     tick(c, PH_GATHER);
 
     // ---- elimination ---------------------------------------------------------
     int k = 0;
-    const bool is_ctl = (tid == c.NWK);
+    const bool is_ctl = c.wm ? (tid == 0) : (tid == c.NWK);
     long long tb1 = (c.prof && tid == 0) ? clock64() : 0;
     for (;;) {
         if (is_ctl) { // retire virgin-unit / empty columns: pure bookkeeping
@@ -421,7 +432,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             c.ctl[CTL_K] = k;
             c.ctl[CTL_NLIST] = 0;
         }
-        __syncthreads(); // B1: updates of the previous step and the position tables are visible
+        csync(c); // B1: updates of the previous step and the position tables are visible
         k = c.ctl[CTL_K];
         long long tq = 0;
         if (c.prof && tid == 0) {
@@ -436,7 +447,10 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
         // non-negative doubles), so no partial results cross warps.
         unsigned bhi = 0u, blo = 0u;
         int bidx = 0x7fffffff;
-        for (int r = lane; r < M; r += 32) {
+        // Small M: every warp scans the whole column (no exchange, one barrier less).
+        // Large M: warps split the rows and exchange one partial each.
+        const bool split = M > 32 * 12;
+        for (int r = split ? tid : lane; r < M; r += split ? c.nthreads : 32) {
             const int pos = c.posOf[r];
             if (pos < k) continue;
             const double v = W[(size_t)r * S + k];
@@ -454,9 +468,27 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                 bidx = packed;
             }
         }
-        const unsigned mh = __reduce_max_sync(kFull, bhi);
-        const unsigned ml = __reduce_max_sync(kFull, bhi == mh ? blo : 0u);
-        const int gi = __reduce_min_sync(kFull, (bhi == mh && blo == ml) ? bidx : 0x7fffffff);
+        unsigned mh = __reduce_max_sync(kFull, bhi);
+        unsigned ml = __reduce_max_sync(kFull, bhi == mh ? blo : 0u);
+        int gi = __reduce_min_sync(kFull, (bhi == mh && blo == ml) ? bidx : 0x7fffffff);
+        if (split) {
+            int *rp = c.red_idx + c.parity * 3 * kMaxWarps;
+            if (lane == 0) {
+                rp[warp] = (int)mh;
+                rp[kMaxWarps + warp] = (int)ml;
+                rp[2 * kMaxWarps + warp] = gi;
+            }
+            csync(c);
+            const bool have = lane < c.nwarps;
+            bhi = have ? (unsigned)rp[lane] : 0u;
+            blo = have ? (unsigned)rp[kMaxWarps + lane] : 0u;
+            bidx = have ? rp[2 * kMaxWarps + lane] : 0x7fffffff;
+            if (bidx == 0x7fffffff) bhi = blo = 0u;
+            mh = __reduce_max_sync(kFull, bhi);
+            ml = __reduce_max_sync(kFull, bhi == mh ? blo : 0u);
+            gi = __reduce_min_sync(kFull, (bhi == mh && blo == ml) ? bidx : 0x7fffffff);
+            c.parity ^= 1;
+        }
         const int pr = gi & 0xffff, ppos = gi >> 16;
         const double pv = W[(size_t)pr * S + k];
         if (c.prof && tid == 0) {
@@ -464,7 +496,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             c.prof[PH_E_SEARCH] += t - tq;
             tq = t;
         }
-        __syncthreads(); // B2: every warp has read the positions it needs for this search
+        csync(c); // B2: every warp has read the positions it needs for this search
         if (c.prof && tid == 0) {
             const long long t = clock64();
             c.prof[PH_E_B2] += t - tq;
@@ -549,63 +581,94 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
     for (int literal = 0; literal < 2; ++literal) {
         back_substitute(c, y, literal != 0);
         if (literal || !c.ctl[CTL_FLAG]) break;
-        __syncthreads();
+        csync(c);
         if (tid == 0) c.ctl[CTL_FLAG] = 0;
     }
 }
 
-template <bool WSMEM>
-__global__ void __launch_bounds__(1024, 1)
-dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
+// HOME: 0 = everything in shared memory, 1 = the working basis W in the HBM
+// workspace, 2 = W and all per-LP vectors in the HBM workspace (large single LPs).
+// WARP: one warp per LP (the CTA is just a bundle of independent warps, each with
+// its own shared-memory slab, workspace slab and work-queue pulls; no CTA barrier
+// is ever executed).  Otherwise one CTA per LP.
+template <int HOME, bool WARP>
+__global__ void __launch_bounds__(WARP ? 128 : 1024, WARP ? 8 : 1)
+dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx c;
     c.M = T.M;
     c.Nn = T.Nn;
     c.S = (T.M + 1) | 1;
-    c.nthreads = blockDim.x;
-    c.nwarps = blockDim.x >> 5;
-    c.G = c.nwarps - 1;
+    c.wm = WARP;
+    c.tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    c.nthreads = WARP ? 32 : (int)blockDim.x;
+    c.nwarps = WARP ? 1 : (int)(blockDim.x >> 5);
+    c.G = WARP ? 1 : c.nwarps - 1;
     c.NWK = c.G * 32;
     c.parity = 0;
-    const int M = c.M, Nn = c.Nn, tid = threadIdx.x;
+    const int M = c.M, Nn = c.Nn, tid = c.tid;
+    const int team_in_cta = WARP ? (int)(threadIdx.x >> 5) : 0;
+    const size_t team = WARP ? (size_t)blockIdx.x * (blockDim.x >> 5) + team_in_cta : (size_t)blockIdx.x;
     {
-        double *dp = reinterpret_cast<double *>(smem_raw);
-        if (WSMEM) {
-            c.W = dp;
-            dp += ((size_t)M * c.S + 1) & ~(size_t)1;
+        double *sp = reinterpret_cast<double *>(smem_raw + (size_t)team_in_cta * smem_per_team);
+        double *gp = Bt.gws + team * Bt.gws_stride;
+        const size_t wsz = ((size_t)M * c.S + 1) & ~(size_t)1;
+        if (HOME == 0) {
+            c.W = sp;
+            sp += wsz;
         } else {
-            c.W = Bt.gws + (size_t)blockIdx.x * Bt.gws_stride;
+            c.W = gp;
+            gp += wsz;
         }
+        // small fixed-size scratch always lives in shared memory (a single warp
+        // needs no reduction scratch)
+        if (!WARP) {
+            c.red_key = sp, sp += 2 * 4 * kMaxWarps;
+        } else {
+            c.red_key = nullptr;
+        }
+        c.prof = Bt.prof ? reinterpret_cast<long long *>(sp) : nullptr;
+        sp += PH_COUNT;
+        int *isp = reinterpret_cast<int *>(sp);
+        if (!WARP) {
+            c.red_idx = isp, isp += 2 * 4 * kMaxWarps;
+        } else {
+            c.red_idx = nullptr;
+        }
+        c.ctl = isp, isp += 8;
+        // vectors indexed by basis position stay in shared memory (HOME <= 1); the
+        // nonbasic-side vectors, touched a handful of times per pivot, move to the
+        // workspace in warp mode so that more warps fit per SM
+        double *dp = (HOME == 2) ? gp : reinterpret_cast<double *>(isp);
         c.x = dp, dp += M;
         c.xb = dp, dp += M;
         c.dxv = dp, dp += M;
         c.vv = dp, dp += M;
-        c.lbuf = dp, dp += M;
-        c.z = dp, dp += Nn;
-        c.zb = dp, dp += Nn;
-        c.dzv = dp, dp += Nn;
-        c.red_key = dp, dp += 2 * 4 * kMaxWarps;
-        c.prof = Bt.prof ? reinterpret_cast<long long *>(dp) : nullptr;
-        dp += PH_COUNT;
+        double *zp = WARP ? gp : dp;
+        c.z = zp, zp += Nn;
+        c.zb = zp, zp += Nn;
+        c.dzv = zp, zp += Nn;
+        int *zip = reinterpret_cast<int *>(zp);
+        c.nb = zip, zip += Nn + (Nn & 1);
+        if (WARP)
+            gp = reinterpret_cast<double *>(zip);
+        else
+            dp = reinterpret_cast<double *>(zip);
         int *ip = reinterpret_cast<int *>(dp);
         c.bas = ip, ip += M;
-        c.nb = ip, ip += Nn;
         c.rowAt = ip, ip += M;
         c.posOf = ip, ip += M;
         c.cnt = ip, ip += M;
         c.unitRow = ip, ip += M;
         c.pend = ip, ip += M;
-        c.rlist = ip, ip += M;
         c.pre = ip, ip += M + 2;
-        c.red_idx = ip, ip += 2 * 4 * kMaxWarps;
-        c.ctl = ip, ip += 8;
     }
     const long long max_pivots = Bt.max_pivots;
 
     for (;;) {
-        __syncthreads();
+        csync(c);
         if (tid == 0) c.ctl[CTL_LP] = (int)atomicAdd(Bt.next_lp, 1u);
-        __syncthreads();
+        csync(c);
         const long long lp = (unsigned)c.ctl[CTL_LP];
         if (lp >= Bt.B) break;
         const double *__restrict__ theta = Bt.theta + (size_t)lp * Bt.n_theta;
@@ -628,7 +691,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
             c.z[k] = -load_ref(theta, T.c_ref[col]);
             c.zb[k] = 1.0;
         }
-        __syncthreads();
+        csync(c);
 
         int status = DZ_OPTIMAL;
         long long pivots = 0, n_primal = 0;
@@ -695,7 +758,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
                         c.n_price += cntp;
                         c.dzv[k] = s;
                     }
-                    __syncthreads();
+                    csync(c);
                     tick(c, PH_PRICE);
                 }
                 if (pass == 0) {
@@ -734,7 +797,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
                 status = DZ_BREAKDOWN; // safe_divide assert, simplex.rs:466
                 break;
             }
-            __syncthreads(); // everyone has read x[p], z[q], ... before they change
+            csync(c); // everyone has read x[p], z[q], ... before they change
             for (int k = tid; k < M; k += c.nthreads) { // fn pivot, simplex.rs:410-421
                 const double d = c.dxv[k];
                 if (k == p) {
@@ -774,12 +837,12 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
             }
             ++pivots;
             if (primal_step) ++n_primal;
-            __syncthreads();
+            csync(c);
             tick(c, PH_UPDATE);
         }
 
         // ---- results: objective_value / solution, simplex.rs:345-371 ----
-        __syncthreads();
+        csync(c);
         if (tid == 0) {
             double obj = 0.0;
             for (int p = 0; p < M; ++p)
@@ -808,7 +871,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
             }
         }
         if (c.prof) {
-            __syncthreads();
+            csync(c);
             if (tid < PH_COUNT) Bt.prof[(size_t)lp * PH_COUNT + tid] = c.prof[tid];
         }
         if (Bt.work) {
@@ -822,22 +885,27 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt) {
     }
 }
 
-size_t smem_bytes_for(int M, int Nn, bool w_in_smem) {
-    const size_t S = (size_t)((M + 1) | 1);
-    size_t doubles = (w_in_smem ? (((size_t)M * S + 1) & ~(size_t)1) : 0) + 5 * (size_t)M +
-                     3 * (size_t)Nn + 2 * 4 * kMaxWarps + PH_COUNT;
-    size_t ints = 8 * (size_t)M + 2 + (size_t)Nn + 2 * 4 * kMaxWarps + 8;
-    return doubles * 8 + ints * 4 + 16;
+size_t zvec_bytes_for(int Nn) { return 3 * (size_t)Nn * 8 + ((size_t)Nn + (Nn & 1)) * 4; }
+size_t pvec_bytes_for(int M) { return 4 * (size_t)M * 8 + (7 * (size_t)M + 2) * 4 + 16; }
+size_t vec_bytes_for(int M, int Nn) { return zvec_bytes_for(Nn) + pvec_bytes_for(M); }
+size_t fixed_smem_bytes(bool warp) {
+    return warp ? PH_COUNT * 8 + 8 * 4 + 16
+                : (2 * 4 * kMaxWarps + PH_COUNT) * 8 + (2 * 4 * kMaxWarps + 8) * 4 + 16;
+}
+size_t w_bytes_for(int M) { return ((((size_t)M * (size_t)((M + 1) | 1)) + 1) & ~(size_t)1) * 8; }
+size_t smem_bytes_for(int M, int Nn, int home) {
+    return fixed_smem_bytes(false) + (home == 0 ? w_bytes_for(M) : 0) +
+           (home <= 1 ? vec_bytes_for(M, Nn) : 0);
 }
 
-template <bool WS>
+template <int HOME, bool WARP>
 cudaError_t launch_one(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan,
                        cudaStream_t st) {
-    auto kern = dz_batch_kernel<WS>;
+    auto kern = dz_batch_kernel<HOME, WARP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          plan.smem_bytes);
     if (e != cudaSuccess) return e;
-    kern<<<plan.grid, plan.block, plan.smem_bytes, st>>>(T, Bt);
+    kern<<<plan.grid, plan.block, plan.smem_bytes, st>>>(T, Bt, plan.smem_per_team);
     return cudaGetLastError();
 }
 
@@ -857,45 +925,75 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t warps_hint
     }
     const size_t max_smem = prop.sharedMemPerBlockOptin;
     const size_t per_sm = prop.sharedMemPerMultiprocessor;
-    const size_t with_w = smem_bytes_for(M, Nn, true);
-    const size_t without = smem_bytes_for(M, Nn, false);
-    if (without > max_smem) {
-        *err = "problem too large for the batched kernel's shared-memory state";
-        return DZ_ERR_LIMIT;
-    }
+    const size_t with_w = smem_bytes_for(M, Nn, 0);
+    const size_t without = smem_bytes_for(M, Nn, 1);
     const int sms = prop.multiProcessorCount;
     // Where the dense working basis lives.  The kernel is bound by dependent-issue
     // latency, so LPs in flight per SM is what buys throughput: with the basis in
     // shared memory only floor(227 KB / (8 M^2)) CTAs fit per SM; with it in an
-    // HBM workspace (L2 resident: grid * 8 M^2 bytes) up to 12 do.  Measured on
-    // config 2 (profiles/): 3.3 kLP/s shared vs 5.1 kLP/s workspace.  Small batches
-    // (fewer LPs than the shared-memory grid) keep the lower-latency shared home.
+    // HBM workspace up to 12 do.  Measured on config 2 (profiles/): 3.3 kLP/s
+    // shared vs 5.1 kLP/s workspace.  Small batches (fewer LPs than the
+    // shared-memory grid) keep the lower-latency shared home.  When even the
+    // per-LP vectors do not fit (M in the thousands) everything moves to HBM.
+    plan->warp_mode = false;
+    plan->smem_per_team = 0;
+    if (warps_hint < 0 && without <= max_smem / 2 && M <= 1024) {
+        // warp-per-LP: WPC independent warps per CTA, basis in the HBM workspace
+        const size_t per_team = (fixed_smem_bytes(true) + pvec_bytes_for(M) + 15) & ~(size_t)15;
+        int wpc = (int)std::min<size_t>(4, max_smem / per_team);
+        wpc = std::max(1, wpc);
+        plan->warp_mode = true;
+        plan->home = 1;
+        plan->tpr = 1;
+        plan->w_in_smem = false;
+        plan->block = 32 * wpc;
+        plan->smem_per_team = (int32_t)per_team;
+        plan->smem_bytes = (int32_t)(per_team * wpc);
+        plan->gws_doubles_per_cta = (int64_t)(((w_bytes_for(M) + zvec_bytes_for(Nn) + 15) & ~(size_t)15) / 8);
+        const int cps_max = std::max(1, std::min((int)(per_sm / ((size_t)plan->smem_bytes + 1024)),
+                                                 2048 / plan->block));
+        int cps = cps_max;
+        if (cps_hint > 0) cps = std::min(cps_max, cps_hint);
+        plan->ctas_per_sm = cps;
+        int64_t grid = (int64_t)sms * cps;
+        const int64_t need = (B + wpc - 1) / wpc;
+        if (grid > need) grid = need;
+        plan->grid = (int32_t)std::max<int64_t>(grid, 1);
+        plan->teams = (int64_t)plan->grid * wpc;
+        return DZ_OK;
+    }
     const int cps_smem = with_w <= max_smem ? (int)(per_sm / (with_w + 1024)) : 0;
-    bool in_smem;
-    if (basis_home == 1)
-        in_smem = cps_smem > 0;
+    int home;
+    if (without > max_smem || basis_home == 3)
+        home = 2;
+    else if (basis_home == 1)
+        home = cps_smem > 0 ? 0 : 1;
     else if (basis_home == 2)
-        in_smem = false;
+        home = 1;
     else
-        in_smem = cps_smem > 0 && (cps_smem >= 6 || B <= (int64_t)sms * cps_smem);
+        home = (cps_smem > 0 && (cps_smem >= 6 || B <= (int64_t)sms * cps_smem)) ? 0 : 1;
     int g = warps_hint > 0 ? warps_hint
-                           : (in_smem ? std::min(8, std::max(2, (M + 31) / 32 + 1))
-                                      : std::min(8, std::max(2, (M + 31) / 32)));
+                           : (home == 0 ? std::min(8, std::max(2, (M + 31) / 32 + 1))
+                                        : std::min(home == 2 ? 31 : 8, std::max(2, (M + 31) / 32)));
+    if (B <= sms && home != 0 && warps_hint <= 0) g = std::min(31, std::max(g, (M + 31) / 32));
     g = std::max(1, std::min(g, 31));
     plan->tpr = g;
+    plan->home = home;
     plan->block = (g + 1) * 32;
-    plan->w_in_smem = in_smem;
-    plan->smem_bytes = (int32_t)(in_smem ? with_w : without);
-    plan->gws_doubles_per_cta = in_smem ? 0 : (((int64_t)M * ((M + 1) | 1) + 1) & ~(int64_t)1);
-    int cps = (int)(per_sm / ((size_t)plan->smem_bytes + 1024));
-    cps = std::max(1, std::min(cps, 2048 / plan->block));
-    cps = std::min(cps, in_smem ? 32 : 12);
-    if (cps_hint > 0) cps = std::min(std::max(1, std::min((int)(per_sm / ((size_t)plan->smem_bytes + 1024)), 2048 / plan->block)), cps_hint);
+    plan->w_in_smem = home == 0;
+    plan->smem_bytes = (int32_t)smem_bytes_for(M, Nn, home);
+    size_t ws = home == 0 ? 0 : w_bytes_for(M) + (home == 2 ? vec_bytes_for(M, Nn) : 0);
+    plan->gws_doubles_per_cta = (int64_t)(((ws + 15) & ~(size_t)15) / 8);
+    const int cps_max = std::max(1, std::min((int)(per_sm / ((size_t)plan->smem_bytes + 1024)),
+                                             2048 / plan->block));
+    int cps = std::min(cps_max, home == 0 ? 32 : 12);
+    if (cps_hint > 0) cps = std::min(cps_max, cps_hint);
     plan->ctas_per_sm = cps;
     int64_t grid = (int64_t)sms * cps;
     if (grid > B) grid = B;
     if (grid < 1) grid = 1;
     plan->grid = (int32_t)grid;
+    plan->teams = grid;
     return DZ_OK;
 }
 
@@ -903,7 +1001,12 @@ int launch_batch(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &pla
                  std::string *err) {
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
-    e = plan.w_in_smem ? launch_one<true>(T, Bt, plan, st) : launch_one<false>(T, Bt, plan, st);
+    if (plan.warp_mode)
+        e = launch_one<1, true>(T, Bt, plan, st);
+    else
+        e = plan.home == 0 ? launch_one<0, false>(T, Bt, plan, st)
+            : plan.home == 1 ? launch_one<1, false>(T, Bt, plan, st)
+                             : launch_one<2, false>(T, Bt, plan, st);
     if (e != cudaSuccess) {
         *err = std::string("dz_batch_kernel launch: ") + cudaGetErrorString(e);
         return DZ_ERR_CUDA;

@@ -124,14 +124,17 @@ typedef struct dz_options {
     int32_t device;       /* CUDA device ordinal                                       */
     int64_t max_pivots;   /* <=0: default watchdog 100*(m+n_int)+1000                  */
     int32_t trace_cap;    /* per-LP pivot trace entries to record (0 = none)           */
-    int32_t worker_warps; /* 0 = auto; warps per CTA working on one LP (tuning knob,
-                             never changes results)                                   */
+    int32_t worker_warps; /* 0 = auto; >0 = CTA per LP with that many worker warps;
+                             -1 = one warp per LP (no CTA barriers).  Tuning knob,
+                             never changes results                                    */
     int32_t ctas_per_sm;  /* 0 = auto                                                  */
     void *stream;         /* cudaStream_t to launch on (NULL = the library's stream)   */
     int32_t profile;      /* 1 = record per-LP phase cycle counts (dz_batch_result.prof) */
     int32_t basis_home;   /* where the dense working basis lives: 0 = auto, 1 = shared
                              memory (lowest latency, few LPs per SM), 2 = HBM/L2
-                             workspace (more LPs in flight per SM)                      */
+                             workspace (more LPs in flight per SM), 3 = basis AND
+                             per-LP vectors in HBM (chosen automatically when they
+                             exceed shared memory: m in the thousands)                 */
 } dz_options;
 void dz_options_default(dz_options *o);
 

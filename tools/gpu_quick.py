@@ -11,7 +11,7 @@ bad = 0
 for wl in sorted(cases.GOLDEN_WORKLOADS):
     w = cases.GOLDEN_WORKLOADS[wl]()
     g = json.load(open(os.path.join(GOLD, wl + ".json")))
-    for G in (0, 1, 3):
+    for G in (0, -1, 3):
         res = solve_batch(Template(w.structure), w.theta, worker_warps=G)
         nb = 0
         for i, e in enumerate(g["lps"]):
@@ -22,7 +22,7 @@ for wl in sorted(cases.GOLDEN_WORKLOADS):
         bad += nb
 w = generate.config2(4096)
 t = Template(w.structure)
-for G in (2, 4, 6, 8):
+for G in (-1, 3):
     b = Batch(t, w.B, worker_warps=G)
     b.upload(w.theta)
     for rep in range(2):
