@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libdantzig_b200.so")
+LIB_PATH = os.environ.get("DZ_LIB", os.path.join(_PKG, "libdantzig_b200.so"))
 
 OK, ERR_ARG, ERR_CUDA, ERR_LIMIT, ERR_ALLOC = 0, -1, -2, -3, -4
 OPTIMAL, UNBOUNDED, INFEASIBLE, BREAKDOWN, PIVOT_CAP = range(5)

@@ -86,7 +86,8 @@ def _check_batch(oracle, w, res, n_oracle, variant):
 
 
 @pytest.mark.parametrize("wl", sorted(cases.GOLDEN_WORKLOADS))
-@pytest.mark.parametrize("shape", [(0, 0), (1, 2), (3, 1)], ids=["auto", "1warp-hbm", "3warps-smem"])
+@pytest.mark.parametrize("shape", [(0, 0), (-1, 0), (1, 2), (3, 1), (2, 3)],
+                         ids=["auto", "warp-per-lp", "cta-1warp-hbm", "cta-3warps-smem", "cta-all-hbm"])
 def test_batch_parity(oracle, wl, shape):
     """Every launch shape (worker warps per LP, home of the working basis) must
     give the same bits: they only change which thread does which operation."""

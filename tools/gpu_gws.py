@@ -2,20 +2,14 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from dantzig_b200 import generate, Template, Batch
-def run(w, **kw):
-    t = Template(w.structure)
-    b = Batch(t, w.B, **kw)
-    b.upload(w.theta); b.solve(); b.sync()
+w = generate.config2(8192)
+t = Template(w.structure)
+for G, cps in ((-1, 2), (-1, 3), (-1, 5)):
+    b = Batch(t, w.B, worker_warps=G, ctas_per_sm=cps)
+    b.upload(w.theta)
+    for rep in range(2):
+        b.solve(); b.sync()
     r = b.download(light=True)
     ms = b.kernel_ms()
-    print(w.name, "B", w.B, kw, b.launch_info(), "ms %.1f" % ms, "LP/s %.1f" % (w.B/ms*1e3), "pivots/s %.0f" % (r.pivots.sum()/ms*1e3), "nonopt", int((r.status != 0).sum()), flush=True)
+    print(os.environ.get("DZ_LIB", "default")[-12:], "c2 B=%d G" % w.B, G, "cps", cps, "ms %.2f" % ms, "LP/s %.0f" % (w.B / ms * 1e3), "nonopt", int((r.status != 0).sum()), flush=True)
     b.close()
-w5 = generate.config5(2368)
-run(w5, worker_warps=-1)
-run(w5, worker_warps=4, ctas_per_sm=8)
-wm = generate.mixed_batch(4096, 20, 40)
-run(wm, worker_warps=-1)
-run(wm)
-ws = generate.small_batch(16384, 8, 16)
-run(ws, worker_warps=-1)
-run(ws)

@@ -25,6 +25,5 @@ def run(w, **kw):
     b.close()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 w = generate.config2(B)
-for tpr in (4, 8):
-    run(w, worker_warps=tpr)
-run(w, worker_warps=4, ctas_per_sm=1)
+run(w, worker_warps=-1, ctas_per_sm=8)
+run(w, worker_warps=-1, ctas_per_sm=2)
