@@ -765,7 +765,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
 // its own shared-memory slab, workspace slab and work-queue pulls; no CTA barrier
 // is ever executed).  Otherwise one CTA per LP.
 template <int HOME, bool WARP>
-__global__ void __launch_bounds__(WARP ? 128 : 1024, WARP ? 4 : 1)
+__global__ void __launch_bounds__(WARP ? 128 : 1024, WARP ? 8 : 1)
 dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx c;
