@@ -145,7 +145,7 @@ struct Ctx {
     unsigned long long n_lu, n_solve, n_price;
 };
 
-enum { CTL_K = 0, CTL_FLAG = 1, CTL_LP = 2, CTL_NLIST = 3 };
+enum { CTL_K = 0, CTL_FLAG = 1, CTL_LP = 2, CTL_NLIST = 3, CTL_RHS0 = 4 };
 
 // Phase slots of the optional per-LP cycle profile (BatchDev::prof).
 enum {
@@ -497,6 +497,8 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
         }
         if (tid == 0) c.ctl[CTL_FLAG] = 0;
         if (warp == c.nwarps - 1) { // exclusive scan of the column lengths (control warp)
+            // pend[p] doubles as the first CSC entry of basis position p until the
+            // back-substitution needs it; CTL_RHS0 is the same for the rhs column
             const int per = (M + 1 + 31) >> 5;
             const int b0 = lane * per;
             int sum = 0;
@@ -505,12 +507,18 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                 int len = 0;
                 if (p < M) {
                     const int col = c.bas[p];
-                    len = T.col_ptr[col + 1] - T.col_ptr[col];
+                    const int e0 = T.col_ptr[col];
+                    len = T.col_ptr[col + 1] - e0;
+                    c.pend[p] = e0;
                 } else if (p == M && !transposed) {
-                    len = T.col_ptr[arg + 1] - T.col_ptr[arg];
+                    const int e0 = T.col_ptr[arg];
+                    len = T.col_ptr[arg + 1] - e0;
+                    c.ctl[CTL_RHS0] = e0;
                 }
+                c.pre[p <= M ? p : M + 1] = len; // lengths first, prefix below
                 sum += len;
             }
+            __syncwarp();
             int incl = sum;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
@@ -520,43 +528,59 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             int run = incl - sum;
             for (int i = 0; i < per; ++i) {
                 const int p = b0 + i;
-                if (p <= M + 1) c.pre[p] = run;
-                int len = 0;
-                if (p < M) {
-                    const int col = c.bas[p];
-                    len = T.col_ptr[col + 1] - T.col_ptr[col];
-                } else if (p == M && !transposed) {
-                    len = T.col_ptr[arg + 1] - T.col_ptr[arg];
+                if (p <= M) {
+                    const int len = c.pre[p];
+                    c.pre[p] = run;
+                    run += len;
                 }
-                run += len;
             }
+            __syncwarp();
             if (lane == 31) c.pre[M + 1] = incl;
         }
     }
     csync(c);
     {
+        // flat enumeration of every entry of every basis column (and of the rhs
+        // column): four independent entries per thread in flight
         const int total = c.pre[M + 1];
-        for (int idx = tid; idx < total; idx += c.nthreads) {
-            // largest p in [0, M] with pre[p] <= idx
-            int lo = 0, hi = M;
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (c.pre[mid] <= idx)
-                    lo = mid;
-                else
-                    hi = mid - 1;
-            }
-            const int p = lo;
-            const int col = (p < M) ? c.bas[p] : arg;
-            const int e = T.col_ptr[col] + (idx - c.pre[p]);
-            const double v = load_ref(theta, T.val_ref[e]);
-            if (v != 0.0) {
-                const int row = T.row_idx[e];
-                if (p == M) {
-                    W[(size_t)row * S + M] = v;
+        for (int base = tid; base < total; base += 4 * c.nthreads) {
+            int pp[4], ee[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = base + q * c.nthreads;
+                int lo = 0, hi = M;
+                if (idx < total) {
+                    while (lo < hi) { // largest p in [0, M] with pre[p] <= idx
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (c.pre[mid] <= idx)
+                            lo = mid;
+                        else
+                            hi = mid - 1;
+                    }
+                    pp[q] = lo;
+                    ee[q] = (lo < M ? c.pend[lo] : c.ctl[CTL_RHS0]) + (idx - c.pre[lo]);
                 } else {
-                    const int wr = transposed ? p : row, wc = transposed ? row : p;
-                    W[(size_t)wr * S + wc] = v;
+                    pp[q] = -1;
+                    ee[q] = 0;
+                }
+            }
+            int ref[4], row[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ref[q] = pp[q] >= 0 ? T.val_ref[ee[q]] : -1;
+                row[q] = pp[q] >= 0 ? T.row_idx[ee[q]] : 0;
+            }
+            double val[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) val[q] = load_ref(theta, ref[q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (pp[q] < 0 || val[q] == 0.0) continue;
+                if (pp[q] == M) {
+                    W[(size_t)row[q] * S + M] = val[q];
+                } else {
+                    const int wr = transposed ? pp[q] : row[q], wc = transposed ? row[q] : pp[q];
+                    W[(size_t)wr * S + wc] = val[q];
                     atomicAdd(&c.cnt[wc], 1);
                     c.unitRow[wc] = wr; // meaningful only where cnt ends at 1
                 }
