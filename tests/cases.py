@@ -23,6 +23,10 @@ GOLDEN_WORKLOADS = {
     # 80x160 mixed: false infeasible (5, 6), safe_divide panic (23), optimal (0);
     # lowered 226x546, too large for shared memory -> exercises the HBM workspace path
     "mixed_80x160_breakdown": lambda: by_ids("mixed80", [5, 6, 23, 0]),
+    # BASELINE.json configs[0]: 100x200 dense, mixed ==/<=/>= rows, 25% free variables
+    # (lowered 283x683).  Seeds 0 and 1: one optimal, one where the reference's own
+    # arithmetic breaks down -- parity includes reproducing that outcome.
+    "c1_100x200": lambda: generate.config1(seeds=(0, 1, 2)),
 }
 
 

@@ -92,6 +92,8 @@ def test_batch_parity(oracle, wl, shape):
     """Every launch shape (worker warps per LP, home of the working basis) must
     give the same bits: they only change which thread does which operation."""
     w = cases.GOLDEN_WORKLOADS[wl]()
+    if w.m >= 100 and shape not in ((0, 0), (2, 3)):
+        pytest.skip("config-1 size: auto and all-in-HBM shapes only (minutes on one warp)")
     t = Template(w.structure)
     res = solve_batch(t, w.theta, trace_cap=256, worker_warps=shape[0], basis_home=shape[1])
     g = json.load(open(os.path.join(GOLD, wl + ".json")))
@@ -102,7 +104,8 @@ def test_batch_parity(oracle, wl, shape):
         assert bits(res.objective[i]) == e["objective_bits"], i
         assert sha(res.values[i]) == e["values_sha"], i
     big = w.m >= 60
-    _check_batch(oracle, w, res, 2 if big else 12, oracle.SKIP if big else oracle.LITERAL)
+    _check_batch(oracle, w, res, (1 if w.m >= 100 else 2) if big else 12,
+                 oracle.SKIP if big else oracle.LITERAL)
 
 
 def test_batch_order_and_resolve_invariance():
