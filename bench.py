@@ -185,8 +185,12 @@ def run_gpu(args) -> None:
     # this rank's shard: LP ids [rank*B, (rank+1)*B) of the config-2 family
     from dantzig_b200.sharding import shard_range
 
-    lo, hi = shard_range(world * B_PER_GPU, rank, world)
-    w = generate.config2(hi - lo, first=lo)
+    per_gpu = args.lps_per_gpu or (B_PER_GPU if args.workload == "c2" else 2048)
+    lo, hi = shard_range(world * per_gpu, rank, world)
+    if args.workload == "c5":      # BASELINE configs[4] unit: m=64 x n=128 (lowered 192x448)
+        w = generate.config5(hi - lo, first=lo)
+    else:                          # BASELINE configs[1]: m=32 x n=64 (lowered 96x224)
+        w = generate.config2(hi - lo, first=lo)
     tmpl = Template(w.structure)
     batch = Batch(tmpl, w.B, device=local)
     pinned = torch.empty(w.theta.shape, dtype=torch.float64).pin_memory()
@@ -280,11 +284,11 @@ def run_gpu(args) -> None:
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"c2_batch_32x64: {B_PER_GPU} independent LPs per GPU, m={M_USER} n={N_USER} "
+                "workload": f"{w.name}: {w.B} independent LPs per GPU, m={w.m} n={w.n} "
                             f"(lowered {tmpl.m}x{tmpl.n_int}), all <= rows, nonneg vars, seed 1234",
-                "sharding": "LP ids [rank*4096,(rank+1)*4096) per rank; no data-path collective; "
+                "sharding": f"LP ids [rank*{w.B},(rank+1)*{w.B}) per rank; no data-path collective; "
                             "final all_gather of status/objective",
-                "l2": "256 MB flush between timed steps (inputs 74 MB < L2)",
+                "l2": f"256 MB flush between timed steps (inputs {w.theta.nbytes / 1e6:.0f} MB)",
                 "launch": info,
                 "status_hist": np.bincount(status_all, minlength=5).tolist(),
                 "pivots_per_step_rank0": pivots,
@@ -308,7 +312,7 @@ def run_gpu(args) -> None:
             "gpu_launches": args.steps,
             "clocks": clocks,
         }
-        if world == 1:
+        if world == 1 and args.workload == "c2":
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
     batch.close()
@@ -341,6 +345,9 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 = BASELINE configs[1] (default), c5 = configs[4] unit shape")
+    ap.add_argument("--lps-per-gpu", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
