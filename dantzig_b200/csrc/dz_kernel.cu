@@ -644,22 +644,42 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
         // Small M: every warp scans the whole column (no exchange, one barrier less).
         // Large M: warps split the rows and exchange one partial each.
         const bool split = M > 32 * 12;
-        for (int r = split ? tid : lane; r < M; r += split ? c.nthreads : 32) {
-            const int pos = c.posOf[r];
-            if (pos < k) continue;
-            const double v = W[(size_t)r * S + k];
-            unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu, lo = (unsigned)__double2loint(v);
-            if (v != v) { // NaN never beats the incumbent, and is never beaten as incumbent
-                if (pos != k) continue;
-                hi = 0xffffffffu;
-                lo = 0xffffffffu;
-            }
-            const int packed = (pos << 16) | r;
-            if (bidx == 0x7fffffff || hi > bhi ||
-                (hi == bhi && (lo > blo || (lo == blo && packed < bidx)))) {
-                bhi = hi;
-                blo = lo;
-                bidx = packed;
+        {
+            // four rows per thread in flight: positions first, then the predicated
+            // column loads as one batch of independent loads
+            const int rstart = split ? tid : lane, rstep = split ? c.nthreads : 32;
+            for (int rb = rstart; rb < M; rb += 4 * rstep) {
+                int pos4[4];
+                double v4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = rb + q * rstep;
+                    pos4[q] = (r < M) ? c.posOf[r] : -1;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = rb + q * rstep;
+                    v4[q] = (pos4[q] >= k) ? W[(size_t)r * S + k] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = rb + q * rstep;
+                    bool cand = pos4[q] >= k;
+                    unsigned hi = (unsigned)__double2hiint(v4[q]) & 0x7fffffffu;
+                    unsigned lo = (unsigned)__double2loint(v4[q]);
+                    if (v4[q] != v4[q]) { // NaN never beats the incumbent, nor is it beaten as one
+                        cand = cand && pos4[q] == k;
+                        hi = 0xffffffffu;
+                        lo = 0xffffffffu;
+                    }
+                    const int packed = (pos4[q] << 16) | r;
+                    const bool better =
+                        cand && (bidx == 0x7fffffff || hi > bhi ||
+                                 (hi == bhi && (lo > blo || (lo == blo && packed < bidx))));
+                    bhi = better ? hi : bhi;
+                    blo = better ? lo : blo;
+                    bidx = better ? packed : bidx;
+                }
             }
         }
         unsigned mh = __reduce_max_sync(kFull, bhi);
@@ -711,7 +731,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             // with a multiplier, a_ij -= l_i * a_kj over the nonzero a_kj (linalg.rs:118-124),
             // four rows in flight.
             const int G = c.G;
-            const double *prow = W + (size_t)pr * S;
+            const double *__restrict__ prow = W + (size_t)pr * S;
             for (int rbase = 0; rbase * G < M; rbase += 32) {
                 const int r_own = (rbase + lane) * G + warp;
                 bool need = false;
@@ -723,43 +743,50 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                         l = __ddiv_rn(v, pv);
                     }
                 }
-                unsigned rows = __ballot_sync(kFull, need);
-                unsigned long long upd = 0;
-                while (rows) {
-                    // peel up to four rows
-                    const int b0 = __ffs(rows) - 1;
-                    rows &= rows - 1;
-                    const int b1 = rows ? __ffs(rows) - 1 : -1;
-                    if (rows) rows &= rows - 1;
-                    const int b2 = rows ? __ffs(rows) - 1 : -1;
-                    if (rows) rows &= rows - 1;
-                    const int b3 = rows ? __ffs(rows) - 1 : -1;
-                    if (rows) rows &= rows - 1;
-                    const double l0 = __shfl_sync(kFull, l, b0);
-                    const double l1 = __shfl_sync(kFull, l, b1 < 0 ? 0 : b1);
-                    const double l2 = __shfl_sync(kFull, l, b2 < 0 ? 0 : b2);
-                    const double l3 = __shfl_sync(kFull, l, b3 < 0 ? 0 : b3);
-                    double *w0 = W + (size_t)((rbase + b0) * G + warp) * S;
-                    double *w1 = W + (size_t)((rbase + (b1 < 0 ? b0 : b1)) * G + warp) * S;
-                    double *w2 = W + (size_t)((rbase + (b2 < 0 ? b0 : b2)) * G + warp) * S;
-                    double *w3 = W + (size_t)((rbase + (b3 < 0 ? b0 : b3)) * G + warp) * S;
-                    for (int c0 = k + 1; c0 <= M; c0 += 32) {
-                        const int j = c0 + lane;
-                        const double u = (j <= M) ? prow[j] : 0.0;
-                        if (u != 0.0) {
-                            const double a0 = w0[j];
-                            const double a1 = (b1 >= 0) ? w1[j] : 0.0;
-                            const double a2 = (b2 >= 0) ? w2[j] : 0.0;
-                            const double a3 = (b3 >= 0) ? w3[j] : 0.0;
-                            w0[j] = __dsub_rn(a0, __dmul_rn(l0, u));
-                            if (b1 >= 0) w1[j] = __dsub_rn(a1, __dmul_rn(l1, u));
-                            if (b2 >= 0) w2[j] = __dsub_rn(a2, __dmul_rn(l2, u));
-                            if (b3 >= 0) w3[j] = __dsub_rn(a3, __dmul_rn(l3, u));
-                            upd += 1 + (b1 >= 0) + (b2 >= 0) + (b3 >= 0);
+                const unsigned rows = __ballot_sync(kFull, need);
+                if (!rows) continue;
+                unsigned long long upd = need ? 1 : 0;
+                // the pivot row four chunks (128 columns) at a time, each batch of loads
+                // independent; two rows of this warp in flight per batch
+                for (int c0 = k + 1; c0 <= M; c0 += 128) {
+                    double u[4];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int j = c0 + lane + 32 * cc;
+                        u[cc] = (j <= M) ? prow[j] : 0.0;
+                    }
+                    unsigned nzu = 0;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) nzu += (u[cc] != 0.0) ? 1u : 0u;
+                    if (!__ballot_sync(kFull, nzu != 0)) continue;
+                    unsigned rr = rows;
+                    while (rr) {
+                        const int b0 = __ffs(rr) - 1;
+                        rr &= rr - 1;
+                        const bool two = rr != 0;
+                        const int b1 = two ? __ffs(rr) - 1 : b0;
+                        if (two) rr &= rr - 1;
+                        const double l0 = __shfl_sync(kFull, l, b0);
+                        const double l1 = __shfl_sync(kFull, l, b1);
+                        double *__restrict__ w0 = W + (size_t)((rbase + b0) * G + warp) * S + c0 + lane;
+                        double *__restrict__ w1 = W + (size_t)((rbase + b1) * G + warp) * S + c0 + lane;
+                        double a0[4], a1[4];
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            a0[cc] = (u[cc] != 0.0) ? w0[32 * cc] : 0.0;
+                            a1[cc] = (two && u[cc] != 0.0) ? w1[32 * cc] : 0.0;
                         }
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            if (u[cc] != 0.0) {
+                                w0[32 * cc] = __dsub_rn(a0[cc], __dmul_rn(l0, u[cc]));
+                                if (two) w1[32 * cc] = __dsub_rn(a1[cc], __dmul_rn(l1, u[cc]));
+                            }
+                        }
+                        upd += 2ull * nzu * (two ? 2 : 1);
                     }
                 }
-                c.n_lu += 2ull * upd + (need ? 1 : 0);
+                c.n_lu += upd;
             }
         }
         if (c.prof && tid == 0) {

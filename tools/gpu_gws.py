@@ -2,14 +2,16 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from dantzig_b200 import generate, Template, Batch
-w = generate.config2(8192)
-t = Template(w.structure)
-for kw in ({"worker_warps": -1, "ctas_per_sm": 4}, {"worker_warps": -1, "ctas_per_sm": 6}, {"worker_warps": -1}):
+def run(w, **kw):
+    t = Template(w.structure)
     b = Batch(t, w.B, **kw)
-    b.upload(w.theta)
-    for rep in range(2):
-        b.solve(); b.sync()
+    b.upload(w.theta); b.solve(); b.sync()
     r = b.download(light=True)
     ms = b.kernel_ms()
-    print(os.environ.get("DZ_LIB", "default")[-12:], "c2 B=%d" % w.B, kw, b.launch_info()["ctas_per_sm"], "ms %.2f" % ms, "LP/s %.0f" % (w.B / ms * 1e3), "nonopt", int((r.status != 0).sum()), flush=True)
+    print(w.name, "B", w.B, kw, b.launch_info(), "ms %.1f" % ms, "LP/s %.1f" % (w.B/ms*1e3), "pivots/s %.0f" % (r.pivots.sum()/ms*1e3), "nonopt", int((r.status != 0).sum()), flush=True)
     b.close()
+w5 = generate.config5(2368)
+run(w5, worker_warps=2, ctas_per_sm=12)
+run(w5, worker_warps=3, ctas_per_sm=12)
+run(w5, worker_warps=-1)
+run(w5, worker_warps=1, ctas_per_sm=12)
