@@ -1202,7 +1202,10 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t warps_hint
         home = (cps_smem > 0 && (cps_smem >= 6 || B <= (int64_t)sms * cps_smem)) ? 0 : 1;
     int g = warps_hint > 0 ? warps_hint
                            : (home == 0 ? std::min(8, std::max(2, (M + 31) / 32 + 1))
-                                        : std::min(home == 2 ? 31 : 8, std::max(2, (M + 31) / 32)));
+                                        : (home == 2 ? std::min(31, std::max(2, (M + 31) / 32))
+                                                     // measured on config 5 (M=192): 3 worker
+                                                     // warps 405 LP/s, 2: 340, 4: 355, 6: 314
+                                                     : std::min(8, std::max(3, (M + 63) / 64))));
     if (B <= sms && home != 0 && warps_hint <= 0) g = std::min(31, std::max(g, (M + 31) / 32));
     g = std::max(1, std::min(g, 31));
     plan->tpr = g;
