@@ -249,15 +249,18 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
             bool has_nz = literal;
             if (!literal) {
                 const double *row = W + (size_t)r * S;
-                for (int j = i + 1; j < M; ++j)
-                    if (row[j] != 0.0) {
-                        has_nz = true;
-                        break;
-                    }
+                for (int j = i + 1; j < M && !has_nz; j += 4) { // four independent loads per trip
+                    const double e0 = row[j];
+                    const double e1 = (j + 1 < M) ? row[j + 1] : 0.0;
+                    const double e2 = (j + 2 < M) ? row[j + 2] : 0.0;
+                    const double e3 = (j + 3 < M) ? row[j + 3] : 0.0;
+                    has_nz = e0 != 0.0 || e1 != 0.0 || e2 != 0.0 || e3 != 0.0;
+                }
             }
             c.pend[i] = has_nz ? 1 : 0;
             if (!has_nz) {
-                const double yi = __ddiv_rn(W[(size_t)r * S + M], W[(size_t)r * S + i]);
+                const double di = W[(size_t)r * S + i], bi = W[(size_t)r * S + M];
+                const double yi = (di == 1.0) ? bi : __ddiv_rn(bi, di); // x/1 is the identity
                 y[i] = yi;
                 if (!isfinite(yi)) c.ctl[CTL_FLAG] = 1;
                 c.n_solve += 1;
@@ -278,23 +281,30 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
                 if (c.prof && lane == 0) c.prof[PH_PENDING] += 1;
                 const double *row = W + (size_t)c.rowAt[i] * S;
                 double s = row[M];
-                for (int j0 = i + 1; j0 < M; j0 += 32) {
-                    const int j = j0 + lane;
-                    double u = 0.0, yj = 0.0;
-                    if (j < M) {
-                        u = row[j];
-                        yj = y[j];
+                const double di = row[i];
+                for (int j0 = i + 1; j0 < M; j0 += 128) { // four chunks of loads in flight
+                    double u4[4], y4[4];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int j = j0 + lane + 32 * cc;
+                        u4[cc] = (j < M) ? row[j] : 0.0;
+                        y4[cc] = (j < M) ? y[j] : 0.0;
                     }
-                    const double t = __dmul_rn(u, yj);
-                    unsigned mk = __ballot_sync(kFull, literal ? (j < M) : (u != 0.0 && yj != 0.0));
-                    if (lane == 0) c.n_solve += 2ull * __popc(mk);
-                    while (mk) {
-                        const int b = __ffs(mk) - 1;
-                        mk &= mk - 1;
-                        s = __dsub_rn(s, __shfl_sync(kFull, t, b));
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int j = j0 + lane + 32 * cc;
+                        const double t = __dmul_rn(u4[cc], y4[cc]);
+                        unsigned mk = __ballot_sync(
+                            kFull, literal ? (j < M) : (u4[cc] != 0.0 && y4[cc] != 0.0));
+                        if (lane == 0) c.n_solve += 2ull * __popc(mk);
+                        while (mk) {
+                            const int b = __ffs(mk) - 1;
+                            mk &= mk - 1;
+                            s = __dsub_rn(s, __shfl_sync(kFull, t, b));
+                        }
                     }
                 }
-                const double yi = __ddiv_rn(s, row[i]);
+                const double yi = (di == 1.0) ? s : __ddiv_rn(s, di);
                 if (lane == 0) {
                     y[i] = yi;
                     if (!isfinite(yi)) c.ctl[CTL_FLAG] = 1;
