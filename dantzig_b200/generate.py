@@ -144,3 +144,52 @@ def packing(B: int, m: int, n: int, first: int = 0) -> Workload:
     st = dense_structure(m, n, senses, has_lb, has_ub)
     th = dense_theta(A, b, c, senses, np.zeros(n), np.zeros(n), has_lb, has_ub, minimize=False)
     return Workload(f"packing_{m}x{n}", st, th, m, n, False, ids)
+
+
+def transportation_model(seed_id: int, n_supply: int, n_demand: int, n_arcs: int, k: int = 1,
+                         seed: int = BASE_SEED, family: int = 4) -> ModelArrays:
+    """Transportation-style sparse LP of BASELINE configs[3]:
+    `n_supply` supply rows (<=), `n_demand` demand rows (>=), one non-negative
+    variable per arc; an arc touches `k` supply rows and `k` demand rows with
+    coefficient +1 (k=1 is the pure transportation form).  Integer supplies and
+    demands built from an integer feasible flow, continuous costs U(1,2).
+    Returned in the MAXIMISE/<= form of dz_model (Minimize negates the costs,
+    >= rows are negated), term order = arc order within each row."""
+    ids = np.array([seed_id], dtype=np.int64)
+    us = uniform(seed, family, ids, 0, n_arcs * k)[0]
+    ud = uniform(seed, family, ids, 1, n_arcs * k)[0]
+    sup = np.minimum((us * n_supply).astype(np.int64), n_supply - 1).reshape(n_arcs, k)
+    dem = np.minimum((ud * n_demand).astype(np.int64), n_demand - 1).reshape(n_arcs, k)
+    x0 = np.minimum((uniform(seed, family, ids, 2, n_arcs)[0] * 5).astype(np.int64), 4)
+    slack = np.minimum((uniform(seed, family, ids, 3, n_supply)[0] * 3).astype(np.int64), 2)
+    cost = 1.0 + uniform(seed, family, ids, 4, n_arcs)[0]
+    rows: list[list[int]] = [[] for _ in range(n_supply + n_demand)]
+    for a in range(n_arcs):
+        for s_ in sorted(set(sup[a].tolist())):
+            rows[s_].append(a)
+        for d_ in sorted(set(dem[a].tolist())):
+            rows[n_supply + d_].append(a)
+    supply = np.zeros(n_supply)
+    demand = np.zeros(n_demand)
+    for a in range(n_arcs):
+        for s_ in set(sup[a].tolist()):
+            supply[s_] += x0[a]
+        for d_ in set(dem[a].tolist()):
+            demand[d_] += x0[a]
+    supply += slack
+    row_ptr = [0]
+    row_var: list[int] = []
+    row_coef: list[float] = []
+    rhs: list[float] = []
+    for r in range(n_supply + n_demand):
+        is_demand = r >= n_supply
+        for a in rows[r]:
+            row_var.append(a)
+            row_coef.append(-1.0 if is_demand else 1.0)     # >= rows are negated
+        row_ptr.append(len(row_var))
+        rhs.append(-float(demand[r - n_supply]) if is_demand else float(supply[r]))
+    return ModelArrays(
+        n_vars=n_arcs, has_lb=np.ones(n_arcs, bool), has_ub=np.zeros(n_arcs, bool),
+        lb=np.zeros(n_arcs), ub=np.zeros(n_arcs),
+        obj_var=np.arange(n_arcs, dtype=np.int32), obj_coef=-cost, obj_const=-0.0,
+        row_ptr=row_ptr, row_var=row_var, row_coef=row_coef, rhs=rhs)

@@ -63,6 +63,32 @@ def test_ragged_models_on_device(oracle, name, model):
         assert bits(s.values[v]) == bits(o.values[k])
 
 
+@pytest.mark.parametrize("shape", [(10, 10, 40, 1), (20, 20, 120, 1), (20, 20, 120, 3)])
+def test_transportation_family_on_device(oracle, shape):
+    """Sparse transportation-style LPs (BASELINE configs[3] family at test size):
+    CSC pricing over 2..6-nonzero columns, almost every elimination step trivial."""
+    from scipy.optimize import linprog
+
+    for seed in range(2):
+        model = generate.transportation_model(seed, *shape)
+        s = solve_model(model)
+        lo = oracle.lower(model)
+        o = lo.solve(oracle.LITERAL)
+        assert (s.status, s.pivots, s.trace_hash, bits(s.objective)) == (
+            o.status, o.pivots, o.trace_hash, bits(o.objective))
+        for k, v in enumerate(lo.orig_var):
+            assert bits(s.values[v]) == bits(o.values[k])
+        # independent optimum (HiGHS) on the same sparse model, max form -> min form
+        n_rows, n = model.n_rows, model.n_vars
+        A = np.zeros((n_rows, n))
+        for r in range(n_rows):
+            for t in range(model.row_ptr[r], model.row_ptr[r + 1]):
+                A[r, model.row_var[t]] = model.row_coef[t]
+        ref = linprog(-model.obj_coef, A_ub=A, b_ub=model.rhs, bounds=[(0, None)] * n, method="highs")
+        assert s.status == 0 and ref.status == 0
+        assert abs(-s.objective - ref.fun) <= 1e-9 * max(1.0, abs(ref.fun))
+
+
 def test_empty_basis_is_breakdown():
     from dantzig_b200.model import ModelBuilder
 

@@ -81,3 +81,11 @@ def test_template_rejects_bad_indices():
     model.obj_var[0] = 5
     with pytest.raises(DzError):
         Template(model)
+
+
+@pytest.mark.parametrize("shape", [(10, 10, 40, 1), (20, 20, 120, 3)])
+def test_lowering_transportation(oracle, shape):
+    """Sparse structure of BASELINE configs[3]: ragged rows, >= rows negated."""
+    from dantzig_b200 import generate
+
+    _check(oracle, generate.transportation_model(0, *shape))
