@@ -67,7 +67,7 @@ struct BatchDev {
 
 // Launch plan computed on the host (dz_kernel.cu).
 struct LaunchPlan {
-    int32_t grid = 0, block = 0, smem_bytes = 0, ctas_per_sm = 0, tpr = 1, home = 0;
+    int32_t grid = 0, block = 0, smem_bytes = 0, ctas_per_sm = 0, worker_warps = 1, home = 0;
     bool w_in_smem = true;
     bool warp_mode = false;    // one warp per LP instead of one CTA per LP
     int32_t smem_per_team = 0; // warp mode: shared-memory slab per warp

@@ -1,11 +1,12 @@
-// dz_kernel.cu -- batched CTA-per-LP parametric self-dual simplex for sm_100a.
+// dz_kernel.cu -- persistent parametric self-dual simplex kernel for sm_100a.
 //
-// One persistent CTA solves one LP at a time (work queue over the batch); the
-// whole pivot loop of Simplex::solve (/root/reference/src/simplex.rs:274-343)
-// runs on the device with no host round trip.  Per pivot the CTA
+// One TEAM (a CTA, or a single warp) solves one LP at a time, pulling LP ids from
+// a work queue; the whole pivot loop of Simplex::solve
+// (/root/reference/src/simplex.rs:274-343) runs on the device with no host round
+// trip.  Per pivot the team
 //   * gathers the basis from the CSC template into a dense working matrix W
-//     held in shared memory (replaces basis_matrix/collect_columns/to_dense/t,
-//     simplex.rs:270-272, linalg.rs:40-48,131-140,188-192),
+//     (replaces basis_matrix/collect_columns/to_dense/t, simplex.rs:270-272,
+//     linalg.rs:40-48,131-140,188-192),
 //   * eliminates [W | rhs] with partial pivoting in the reference's exact
 //     operation order (Matrix::factorize linalg.rs:88-128 fused with the forward
 //     half of LU::solve linalg.rs:286-291), once for B and once for B^T,
@@ -29,17 +30,29 @@
 //   * L is never stored: the right-hand side rides along as column M of W, so
 //     the forward substitution happens inside the elimination;
 //   * rows are never physically swapped: a logical-position table records the
-//     interchanges (positions decide the pivot-search tie-break).
+//     interchanges (positions decide the pivot-search tie-break);
+//   * division by an exact 1.0 (every slack pivot) is the identity and is elided.
 // When a back-substitution produces a non-finite value the skipping rules are
 // no longer no-ops (0*inf = NaN), so that solve is redone without skipping.
 //
-// THREAD MAP.  G worker warps + one control warp per CTA.  In the pivot search
-// and the multiplier computation worker threads stand for rows (column access,
-// odd row stride => conflict free); in the trailing update warps take rows of
-// the compact list of rows with a nonzero multiplier and lanes take columns
-// (row access, contiguous), four rows in flight per warp.  The control warp
-// retires the virgin-unit steps, keeps the position tables and runs the serial
-// part of back-substitution.  Two CTA barriers per non-trivial step.
+// LAUNCH SHAPES (template <HOME, WARP>, chosen by plan_launch; all bit-identical):
+//   WARP=1          one warp per LP, W in the HBM workspace, no CTA barrier at all
+//                   (default for large batches with m_int <= 128: config 2);
+//   WARP=0, HOME=0  CTA per LP (G worker warps + a control warp), W and the per-LP
+//                   vectors in shared memory (single LPs / small batches);
+//   WARP=0, HOME=1  CTA per LP, W in the HBM workspace (config 5, config 1);
+//   WARP=0, HOME=2  CTA per LP, W and all per-LP vectors in HBM (config 3).
+// The kernel is bound by dependent load/issue latency per LP, so throughput comes
+// from LPs in flight per SM and from fetching operands as batches of independent
+// loads (DESIGN.md section 4 has the measurements).
+//
+// THREAD MAP of an elimination step.  Pivot search: every warp scans the whole
+// pivot column (threads stand for rows; warps split the rows when m_int > 384)
+// and reduces the bit patterns of |v| with REDUX.  Multipliers: worker warp w
+// owns rows lane*G + w.  Trailing update: lanes take columns (row-contiguous
+// access), rows with a nonzero multiplier go two at a time.  The control thread
+// records interchanges and runs ahead over virgin-unit steps; it and the serial
+// part of back-substitution live on the control warp (the warp itself if WARP).
 
 #include "dz_internal.h"
 
@@ -145,7 +158,7 @@ struct Ctx {
     unsigned long long n_lu, n_solve, n_price;
 };
 
-enum { CTL_K = 0, CTL_FLAG = 1, CTL_LP = 2, CTL_NLIST = 3, CTL_RHS0 = 4 };
+enum { CTL_K = 0, CTL_FLAG = 1, CTL_LP = 2, CTL_RHS0 = 3 };
 
 // Phase slots of the optional per-LP cycle profile (BatchDev::prof).
 enum {
@@ -629,7 +642,6 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                 break;
             }
             c.ctl[CTL_K] = k;
-            c.ctl[CTL_NLIST] = 0;
         }
         csync(c); // B1: updates of the previous step and the position tables are visible
         k = c.ctl[CTL_K];
@@ -1182,7 +1194,7 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t warps_hint
         wpc = std::max(1, wpc);
         plan->warp_mode = true;
         plan->home = 1;
-        plan->tpr = 1;
+        plan->worker_warps = 1;
         plan->w_in_smem = false;
         plan->block = 32 * wpc;
         plan->smem_per_team = (int32_t)per_team;
@@ -1218,7 +1230,7 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t warps_hint
                                                      : std::min(8, std::max(3, (M + 63) / 64))));
     if (B <= sms && home != 0 && warps_hint <= 0) g = std::min(31, std::max(g, (M + 31) / 32));
     g = std::max(1, std::min(g, 31));
-    plan->tpr = g;
+    plan->worker_warps = g;
     plan->home = home;
     plan->block = (g + 1) * 32;
     plan->w_in_smem = home == 0;
