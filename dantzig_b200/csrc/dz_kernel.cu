@@ -337,27 +337,28 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
 // independent loads and the NEXT row prefetched while the current chain runs.
 // Products with an exact-zero factor are skipped unless `literal`; division by an
 // exact 1.0 (every slack pivot) is the identity and is elided.
+template <int NR>
 __device__ __forceinline__ void warp_back_substitute_small(Ctx &c, double *y, const bool literal) {
     const int M = c.M, S = c.S, lane = c.tid;
     const double *__restrict__ W = c.W;
-    double uu[4], nu[4], d = 0.0, rhs = 0.0, nd = 0.0, nrhs = 0.0;
+    double uu[NR], nu[NR], d = 0.0, rhs = 0.0, nd = 0.0, nrhs = 0.0;
     {
         const double *rowp = W + (size_t)c.rowAt[M - 1] * S;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) nu[cc] = 0.0;
+        for (int cc = 0; cc < NR; ++cc) nu[cc] = 0.0;
         nd = rowp[M - 1];
         nrhs = rowp[M];
     }
     unsigned long long ops = 0;
     for (int i = M - 1; i >= 0; --i) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) uu[cc] = nu[cc];
+        for (int cc = 0; cc < NR; ++cc) uu[cc] = nu[cc];
         d = nd;
         rhs = nrhs;
         if (i > 0) { // prefetch row i-1 (its U entries do not depend on y)
             const double *rowp = W + (size_t)c.rowAt[i - 1] * S;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < NR; ++cc) {
                 const int j = i + lane + 32 * cc;
                 nu[cc] = (j < M) ? rowp[j] : 0.0;
             }
@@ -366,7 +367,7 @@ __device__ __forceinline__ void warp_back_substitute_small(Ctx &c, double *y, co
         }
         double s = rhs;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < NR; ++cc) {
             const int j = i + 1 + lane + 32 * cc;
             if (i + 1 + 32 * cc >= M) break;
             const double yj = (j < M) ? y[j] : 0.0;
@@ -392,31 +393,32 @@ __device__ __forceinline__ void warp_back_substitute_small(Ctx &c, double *y, co
     tick(c, PH_BACK_B);
 }
 
-// One elimination step of the warp-per-LP mode for M <= 128 (at most four rows and
-// four pivot-row chunks per lane).  Same arithmetic as the general step below; the
+// One elimination step of the warp-per-LP mode for M <= 32*NR <= 128 (at most NR rows
+// and NR pivot-row chunks per lane).  Same arithmetic as the general step below; the
 // point is memory-level parallelism: the column, the pivot row and the rows to
 // update are fetched with batches of independent loads (the basis lives in the
 // HBM/L2 workspace, ~0.3-0.8 us away) instead of one dependent load at a time,
 // and the values read by the pivot search are reused for the multipliers.
+template <int NR>
 __device__ __forceinline__ void warp_step_small(Ctx &c, double *__restrict__ W, const int k,
                                                 const bool is_ctl) {
     const int M = c.M, S = c.S, lane = c.tid;
-    int pos[4];
-    double v[4];
+    int pos[NR];
+    double v[NR];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NR; ++i) {
         const int r = lane + 32 * i;
         pos[i] = (r < M) ? c.posOf[r] : -1;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NR; ++i) {
         const int r = lane + 32 * i;
         v[i] = (pos[i] >= k) ? W[(size_t)r * S + k] : 0.0;
     }
     unsigned bhi = 0u, blo = 0u;
     int bidx = 0x7fffffff;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NR; ++i) {
         const int r = lane + 32 * i;
         bool cand = pos[i] >= k;
         unsigned hi = (unsigned)__double2hiint(v[i]) & 0x7fffffffu, lo = (unsigned)__double2loint(v[i]);
@@ -439,9 +441,9 @@ __device__ __forceinline__ void warp_step_small(Ctx &c, double *__restrict__ W, 
     const double *__restrict__ prow = W + (size_t)pr * S;
     const double pv = prow[k];
     // pivot row, up to four chunks of 32 columns (column M is the right-hand side)
-    double u[4];
+    double u[NR];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
+    for (int cc = 0; cc < NR; ++cc) {
         const int j = k + 1 + lane + 32 * cc;
         u[cc] = (j <= M) ? prow[j] : 0.0;
     }
@@ -457,10 +459,10 @@ __device__ __forceinline__ void warp_step_small(Ctx &c, double *__restrict__ W, 
     if (pv == 0.0) return; // linalg.rs:117
     unsigned nzu = 0;
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) nzu += (u[cc] != 0.0) ? 1u : 0u;
+    for (int cc = 0; cc < NR; ++cc) nzu += (u[cc] != 0.0) ? 1u : 0u;
     unsigned long long upd = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NR; ++i) {
         const int r = lane + 32 * i;
         const bool need = pos[i] >= k && r != pr && v[i] != 0.0;
         unsigned rows = __ballot_sync(kFull, need);
@@ -477,14 +479,14 @@ __device__ __forceinline__ void warp_step_small(Ctx &c, double *__restrict__ W, 
             double *__restrict__ w0 = W + (size_t)(b0 + 32 * i) * S + k + 1 + lane;
             double *__restrict__ w1 = W + (size_t)((b1 < 0 ? b0 : b1) + 32 * i) * S + k + 1 + lane;
             const bool two = b1 >= 0;
-            double a0[4], a1[4];
+            double a0[NR], a1[NR];
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < NR; ++cc) {
                 a0[cc] = (u[cc] != 0.0) ? w0[32 * cc] : 0.0;
                 a1[cc] = (two && u[cc] != 0.0) ? w1[32 * cc] : 0.0;
             }
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < NR; ++cc) {
                 if (u[cc] != 0.0) {
                     w0[32 * cc] = __dsub_rn(a0[cc], __dmul_rn(l0, u[cc]));
                     if (two) w1[32 * cc] = __dsub_rn(a1[cc], __dmul_rn(l1, u[cc]));
@@ -651,8 +653,15 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             c.prof[PH_E_B1] += tq - tb1;
         }
         if (k >= M - 1) break;
-        if (c.wm && M <= 128) { // warp-per-LP fast path (batched loads)
-            warp_step_small(c, W, k, is_ctl);
+        if (c.wm && M <= 128) { // warp-per-LP fast path (batched loads), NR = ceil(M/32)
+            if (M <= 32)
+                warp_step_small<1>(c, W, k, is_ctl);
+            else if (M <= 64)
+                warp_step_small<2>(c, W, k, is_ctl);
+            else if (M <= 96)
+                warp_step_small<3>(c, W, k, is_ctl);
+            else
+                warp_step_small<4>(c, W, k, is_ctl);
             ++k;
             continue;
         }
@@ -822,8 +831,14 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
     // ---- back substitution ------------------------------------------------------
     // (second trip only when a non-finite value appeared: redo without skipping)
     for (int literal = 0; literal < 2; ++literal) {
-        if (c.wm && M <= 128)
-            warp_back_substitute_small(c, y, literal != 0);
+        if (c.wm && M <= 32)
+            warp_back_substitute_small<1>(c, y, literal != 0);
+        else if (c.wm && M <= 64)
+            warp_back_substitute_small<2>(c, y, literal != 0);
+        else if (c.wm && M <= 96)
+            warp_back_substitute_small<3>(c, y, literal != 0);
+        else if (c.wm && M <= 128)
+            warp_back_substitute_small<4>(c, y, literal != 0);
         else
             back_substitute(c, y, literal != 0);
         if (literal || !c.ctl[CTL_FLAG]) break;
