@@ -89,6 +89,67 @@ def test_transportation_family_on_device(oracle, shape):
         assert abs(-s.objective - ref.fun) <= 1e-9 * max(1.0, abs(ref.fun))
 
 
+def test_random_ragged_models_on_device(oracle):
+    """Fuzz: random small models with duplicate terms, explicit zeros, empty rows,
+    boxed / free / non-positive variables, integer data (ties everywhere).  Every
+    outcome of the reference -- optimal, unbounded, infeasible, breakdown -- must be
+    reproduced with the same pivot trace."""
+    from dantzig_b200.model import ModelBuilder
+
+    rng = np.random.default_rng(20261018)
+    seen = np.zeros(5, int)
+    for _ in range(150):
+        mb = ModelBuilder()
+        nv = int(rng.integers(1, 8))
+        vs = [mb.var(lb=[None, 0.0, -1.5][rng.integers(3)], ub=[None, 2.5, 4.0][rng.integers(3)])
+              for _ in range(nv)]
+        pick = lambda k: [(float(rng.integers(-3, 4)), vs[rng.integers(nv)]) for _ in range(k)]
+        mb.maximize(pick(int(rng.integers(0, 5))), float(rng.integers(-2, 3)))
+        for _ in range(int(rng.integers(0, 7))):
+            [mb.leq, mb.geq, mb.eq][rng.integers(3)](pick(int(rng.integers(0, 5))), float(rng.integers(-4, 5)))
+        model = mb.build()
+        if len(model.obj_var) + len(model.row_var) == 0:
+            continue
+        lo = oracle.lower(model)
+        o = lo.solve(oracle.LITERAL, max_pivots=2000)
+        s = solve_model(model, max_pivots=2000)
+        seen[o.status] += 1
+        assert (s.status, s.pivots, s.trace_hash) == (o.status, o.pivots, o.trace_hash), model
+        assert bits(s.objective) == bits(o.objective) or (s.objective != s.objective and o.objective != o.objective)
+        for k, v in enumerate(lo.orig_var):
+            assert bits(s.values[v]) == bits(o.values[k]) or (s.values[v] != s.values[v] and o.values[k] != o.values[k])
+    assert seen[0] > 20 and seen[1] > 5 and seen[2] > 5      # the fuzz reaches all outcomes
+
+
+@pytest.mark.parametrize("shape", [(-1, 0), (2, 1), (2, 2)], ids=["warp", "cta-smem", "cta-hbm"])
+def test_integer_data_batches(oracle, shape):
+    """Degenerate batches: small-integer coefficients make ties in every pivot
+    search and ratio test, exact zeros in the data, infeasible and unbounded LPs."""
+    from dantzig_b200.model import dense_structure, dense_theta
+
+    rng = np.random.default_rng(7)
+    B, m, n = 96, 7, 10
+    A = rng.integers(-2, 3, size=(B, m, n)).astype(np.float64)
+    b = rng.integers(-1, 6, size=(B, m)).astype(np.float64)
+    c = rng.integers(-3, 4, size=(B, n)).astype(np.float64)
+    senses = np.array([0, 1, 2, 0, 0, 1, 0], np.int32)
+    has_lb = np.array([j % 3 != 2 for j in range(n)])
+    has_ub = np.array([j % 4 == 1 for j in range(n)])
+    lb, ub = np.zeros(n), np.full(n, 3.0)
+    st = dense_structure(m, n, senses, has_lb, has_ub)
+    th = dense_theta(A, b, c, senses, lb, ub, has_lb, has_ub, minimize=True)
+    t = Template(st)
+    res = solve_batch(t, th, trace_cap=64, worker_warps=shape[0], basis_home=shape[1], max_pivots=500)
+    hist = np.zeros(5, int)
+    for i in range(B):
+        o = oracle.lower(model_from_theta(st, th[i])).solve(oracle.LITERAL, max_pivots=500, trace_cap=64)
+        hist[o.status] += 1
+        assert (res.status[i], res.pivots[i], int(res.trace_hash[i])) == (o.status, o.pivots, o.trace_hash), i
+        assert np.array_equal(res.trace[i, : min(o.pivots, 64)], o.trace), i
+        assert bits(res.objective[i]) == bits(o.objective) or o.objective != o.objective, i
+    assert hist[0] > 0 and hist[1] + hist[2] > 0
+
+
 def test_empty_basis_is_breakdown():
     from dantzig_b200.model import ModelBuilder
 
