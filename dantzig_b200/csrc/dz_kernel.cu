@@ -500,6 +500,7 @@ __device__ __forceinline__ void warp_step_small(Ctx &c, double *__restrict__ W, 
 
 // lu_solve (linalg.rs:8-10) of B (transposed == false, rhs = column `arg` of A)
 // or of B^T (transposed == true, rhs = e_arg).  Result in y[0..M).
+template <int WARP_NR_MAX>
 __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                                             const double *__restrict__ theta, bool transposed,
                                             int arg, double *y) {
@@ -653,15 +654,24 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             c.prof[PH_E_B1] += tq - tb1;
         }
         if (k >= M - 1) break;
-        if (c.wm && M <= 128) { // warp-per-LP fast path (batched loads), NR = ceil(M/32)
-            if (M <= 32)
-                warp_step_small<1>(c, W, k, is_ctl);
-            else if (M <= 64)
-                warp_step_small<2>(c, W, k, is_ctl);
-            else if (M <= 96)
-                warp_step_small<3>(c, W, k, is_ctl);
-            else
-                warp_step_small<4>(c, W, k, is_ctl);
+        if (c.wm && M <= 32 * WARP_NR_MAX) { // warp-per-LP fast path, NR = ceil(M/32)
+            if (WARP_NR_MAX <= 4) {
+                if (M <= 32)
+                    warp_step_small<1>(c, W, k, is_ctl);
+                else if (M <= 64)
+                    warp_step_small<2>(c, W, k, is_ctl);
+                else if (M <= 96)
+                    warp_step_small<3>(c, W, k, is_ctl);
+                else
+                    warp_step_small<4>(c, W, k, is_ctl);
+            } else {
+                if (M <= 160)
+                    warp_step_small<5>(c, W, k, is_ctl);
+                else if (M <= 192)
+                    warp_step_small<6>(c, W, k, is_ctl);
+                else
+                    warp_step_small<8>(c, W, k, is_ctl);
+            }
             ++k;
             continue;
         }
@@ -831,14 +841,20 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
     // ---- back substitution ------------------------------------------------------
     // (second trip only when a non-finite value appeared: redo without skipping)
     for (int literal = 0; literal < 2; ++literal) {
-        if (c.wm && M <= 32)
+        if (c.wm && WARP_NR_MAX <= 4 && M <= 32)
             warp_back_substitute_small<1>(c, y, literal != 0);
-        else if (c.wm && M <= 64)
+        else if (c.wm && WARP_NR_MAX <= 4 && M <= 64)
             warp_back_substitute_small<2>(c, y, literal != 0);
-        else if (c.wm && M <= 96)
+        else if (c.wm && WARP_NR_MAX <= 4 && M <= 96)
             warp_back_substitute_small<3>(c, y, literal != 0);
-        else if (c.wm && M <= 128)
+        else if (c.wm && WARP_NR_MAX <= 4 && M <= 128)
             warp_back_substitute_small<4>(c, y, literal != 0);
+        else if (c.wm && WARP_NR_MAX > 4 && M <= 160)
+            warp_back_substitute_small<5>(c, y, literal != 0);
+        else if (c.wm && WARP_NR_MAX > 4 && M <= 192)
+            warp_back_substitute_small<6>(c, y, literal != 0);
+        else if (c.wm && WARP_NR_MAX > 4 && M <= 256)
+            warp_back_substitute_small<8>(c, y, literal != 0);
         else
             back_substitute(c, y, literal != 0);
         if (literal || !c.ctl[CTL_FLAG]) break;
@@ -852,8 +868,10 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
 // WARP: one warp per LP (the CTA is just a bundle of independent warps, each with
 // its own shared-memory slab, workspace slab and work-queue pulls; no CTA barrier
 // is ever executed).  Otherwise one CTA per LP.
-template <int HOME, bool WARP>
-__global__ void __launch_bounds__(WARP ? 128 : 1024, WARP ? 8 : 1)
+// NRMAX: largest ceil(m_int/32) the warp fast paths are instantiated for: 4 (64
+// registers, 32 warps per SM) or 8 (128 registers, 16 warps per SM: config 5).
+template <int HOME, bool WARP, int NRMAX>
+__global__ void __launch_bounds__(WARP ? 128 : 1024, WARP ? (NRMAX <= 4 ? 8 : 4) : 1)
 dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx c;
@@ -998,8 +1016,8 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
             bool failed = false;
             for (int pass = 0; pass < 2; ++pass) {
                 const bool transposed = (pass == 0) != primal_step;
-                basis_solve(c, T, theta, transposed, transposed ? p : c.nb[q],
-                            transposed ? c.vv : c.dxv);
+                basis_solve<NRMAX>(c, T, theta, transposed, transposed ? p : c.nb[q],
+                                   transposed ? c.vv : c.dxv);
                 if (transposed) {
                     // pricing: dz = -N^T v (simplex.rs:235, linalg.rs:199-207); each
                     // column is summed sequentially in ascending row order
@@ -1159,10 +1177,10 @@ size_t smem_bytes_for(int M, int Nn, int home) {
            (home <= 1 ? vec_bytes_for(M, Nn) : 0);
 }
 
-template <int HOME, bool WARP>
+template <int HOME, bool WARP, int NRMAX>
 cudaError_t launch_one(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan,
                        cudaStream_t st) {
-    auto kern = dz_batch_kernel<HOME, WARP>;
+    auto kern = dz_batch_kernel<HOME, WARP, NRMAX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          plan.smem_bytes);
     if (e != cudaSuccess) return e;
@@ -1270,11 +1288,11 @@ int launch_batch(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &pla
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     if (plan.warp_mode)
-        e = launch_one<1, true>(T, Bt, plan, st);
+        e = T.M <= 128 ? launch_one<1, true, 4>(T, Bt, plan, st) : launch_one<1, true, 8>(T, Bt, plan, st);
     else
-        e = plan.home == 0 ? launch_one<0, false>(T, Bt, plan, st)
-            : plan.home == 1 ? launch_one<1, false>(T, Bt, plan, st)
-                             : launch_one<2, false>(T, Bt, plan, st);
+        e = plan.home == 0 ? launch_one<0, false, 4>(T, Bt, plan, st)
+            : plan.home == 1 ? launch_one<1, false, 4>(T, Bt, plan, st)
+                             : launch_one<2, false, 4>(T, Bt, plan, st);
     if (e != cudaSuccess) {
         *err = std::string("dz_batch_kernel launch: ") + cudaGetErrorString(e);
         return DZ_ERR_CUDA;

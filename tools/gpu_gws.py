@@ -10,8 +10,12 @@ def run(w, **kw):
     ms = b.kernel_ms()
     print(w.name, "B", w.B, kw, b.launch_info(), "ms %.1f" % ms, "LP/s %.1f" % (w.B/ms*1e3), "pivots/s %.0f" % (r.pivots.sum()/ms*1e3), "nonopt", int((r.status != 0).sum()), flush=True)
     b.close()
+    return r
 w5 = generate.config5(2368)
-run(w5, worker_warps=2, ctas_per_sm=12)
-run(w5, worker_warps=3, ctas_per_sm=12)
-run(w5, worker_warps=-1)
-run(w5, worker_warps=1, ctas_per_sm=12)
+a = run(w5, worker_warps=-1)
+b = run(w5, worker_warps=3, ctas_per_sm=12)
+print("same results:", np.array_equal(a.trace_hash, b.trace_hash), np.array_equal(a.objective, b.objective, equal_nan=True), np.array_equal(a.status, b.status))
+w = generate.mixed_batch(64, 50, 100)   # M = 141 -> NR 5
+t = Template(w.structure); print("mixed_50x100 lowered", t.m)
+a = run(w, worker_warps=-1); b = run(w, worker_warps=3, basis_home=2)
+print("same results:", np.array_equal(a.trace_hash, b.trace_hash), np.array_equal(a.status, b.status))
