@@ -245,3 +245,31 @@ def measure_fp64_peak(device: int = 0) -> tuple[float, float]:
     a, b = C.c_double(), C.c_double()
     _capi.check(_capi.lib().dz_measure_fp64_peak(device, C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def solve_dense_batch(A, b, c, senses, lb=None, ub=None, *, minimize: bool = True, **kw):
+    """Array-native batched front door: B dense LPs of one shape,
+
+        min / max  c[i] . x   s.t.  A[i] x  (senses)  b[i],   lb <= x <= ub,
+
+    with `senses[r]` in {LE, GE, EQ} and `lb`/`ub` entries of +-inf or None
+    meaning "no bound" (shared by the batch).  Lowered exactly the way the
+    reference frontend lowers the same model (see model.py), solved on the GPU.
+    Returns (status[B], objective[B] in the caller's sense, x[B, n], BatchResult).
+    """
+    from .model import dense_structure, dense_theta
+
+    A = np.asarray(A, dtype=np.float64)
+    if A.ndim == 2:
+        A = A[None]
+    B, m, n = A.shape
+    lb = np.zeros(n) if lb is None else np.asarray([-np.inf if v is None else v for v in lb], float)
+    ub = np.full(n, np.inf) if ub is None else np.asarray([np.inf if v is None else v for v in ub], float)
+    has_lb, has_ub = np.isfinite(lb), np.isfinite(ub)
+    structure = dense_structure(m, n, senses, has_lb, has_ub)
+    theta = dense_theta(A, np.asarray(b, float).reshape(B, m), np.asarray(c, float).reshape(B, n),
+                        senses, np.where(has_lb, lb, 0.0), np.where(has_ub, ub, 0.0), has_lb, has_ub,
+                        minimize=minimize)
+    res = solve_batch(Template(structure), theta, **kw)
+    objective = -res.objective if minimize else res.objective
+    return res.status, objective, res.values, res

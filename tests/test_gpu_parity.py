@@ -150,6 +150,35 @@ def test_integer_data_batches(oracle, shape):
     assert hist[0] > 0 and hist[1] + hist[2] > 0
 
 
+def test_array_native_front_door():
+    """solve_dense_batch: mixed senses, boxed/free variables, against HiGHS."""
+    from scipy.optimize import linprog
+
+    from dantzig_b200 import EQ, GE, LE, solve_dense_batch
+
+    rng = np.random.default_rng(3)
+    B, m, n = 16, 6, 9
+    A = rng.uniform(-1, 1, (B, m, n))
+    x0 = rng.uniform(0.2, 0.8, (B, n))
+    senses = np.array([LE, GE, EQ, LE, LE, GE], np.int32)
+    slack = np.where(senses == LE, 0.3, np.where(senses == GE, -0.3, 0.0))
+    b = np.einsum("bij,bj->bi", A, x0) + slack
+    c = rng.uniform(-1, 1, (B, n))
+    lb = [0.0] * n
+    ub = [1.0] * n
+    ub[4] = None                         # x4 unbounded above
+    status, obj, x, _ = solve_dense_batch(A, b, c, senses, lb, ub, minimize=True)
+    for i in range(B):
+        a_ub = np.vstack([A[i][senses == LE], -A[i][senses == GE]])
+        b_ub = np.concatenate([b[i][senses == LE], -b[i][senses == GE]])
+        ref = linprog(c[i], A_ub=a_ub, b_ub=b_ub, A_eq=A[i][senses == EQ], b_eq=b[i][senses == EQ],
+                      bounds=[(l, u) for l, u in zip(lb, ub)], method="highs")
+        if ref.status == 0 and status[i] == 0:
+            assert abs(obj[i] - ref.fun) <= 1e-9 * max(1.0, abs(ref.fun))
+        else:
+            assert {0: 0, 2: 2, 3: 1}.get(ref.status, -1) == status[i] or status[i] == 3
+
+
 def test_empty_basis_is_breakdown():
     from dantzig_b200.model import ModelBuilder
 
