@@ -320,3 +320,60 @@ def test_rust_module_end_to_end():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def _frontend(rs):
+    import sys
+    import types
+
+    if "dantzig.exceptions" not in sys.modules:
+        exc = types.ModuleType("dantzig.exceptions")
+        exc.UnboundedError = type("UnboundedError", (Exception,), {})
+        exc.InfeasibleError = type("InfeasibleError", (Exception,), {})
+        pkg = types.ModuleType("dantzig")
+        pkg.exceptions = exc
+        sys.modules["dantzig"], sys.modules["dantzig.exceptions"] = pkg, exc
+    sys.modules.setdefault("dantzig.rust", rs)
+    from tests.frontend_shim import bind
+
+    return bind(rs) + (sys.modules["dantzig.exceptions"],)
+
+
+def test_reference_python_tests_through_the_module():
+    """The reference's tests/test_optimize.py and tests/test_exceptions.py, driven
+    through the drop-in module with the call sequence the reference frontend makes
+    (tests/frontend_shim.py), solved on the GPU, asserted with exact ==."""
+    import dantzig_b200.rust as rs
+
+    Var, minimize, maximize, exc = _frontend(rs)
+    x, y = Var.nonneg(), Var.nonneg()                                    # test_problem_1
+    s = minimize(2 * x - 2 * y, [y == 3])
+    assert (s.objective_value, s[x], s[y]) == (-6.0, 0.0, 3.0)
+    x, y = Var.nonneg(), Var.nonneg()                                    # test_problem_2
+    s = minimize(2 * x - 2 * y, [y <= 5, x >= y + 1, y == 5.0])
+    assert (s.objective_value, s[x], s[y]) == (2.0, 6.0, 5.0)
+    x, y, z = Var.nonneg(), Var.nonneg(), Var.nonneg()                   # test_problem_3
+    s = minimize(x + y - z, [x + y + z <= 1])
+    assert (s.objective_value, s[x], s[y], s[z]) == (-1.0, 0.0, 0.0, 1.0)
+    x, y, z = Var.nonneg(), Var.nonneg(), Var.nonneg()                   # test_problem_4
+    s = minimize(x + y + z, [x - y == -2])
+    assert (s.objective_value, s[x], s[y], s[z]) == (2.0, 0.0, 2.0, 0.0)
+    x, y = Var.nonneg(), Var.nonneg()                                    # min/max equivalence
+    a, b = minimize(-x, [x + y <= 1]), maximize(x, [x + y <= 1])
+    assert a.objective_value == -1.0 == -b.objective_value and a[x] == 1.0 == b[x] and a[y] == 0.0 == b[y]
+    x, y, z = Var(lb=-2.0, ub=2.0), Var.free(), Var.nonpos()             # non standard variables
+    s = minimize(x + y + z, [y == 4, x <= 3.0, z >= -1])
+    assert (s.objective_value, s[x], s[y], s[z]) == (1.0, -2.0, 4.0, -1.0)
+    p, h, d = [0.5, 3.5, 5.0], [1.0, 5.5, 1.5], [50, 75, 100]           # inventory balance
+    xs, zs = [Var.nonneg() for _ in range(3)], [Var.nonneg() for _ in range(3)]
+    cost = sum(pt * xt for pt, xt in zip(p, xs)) + sum(ht * zt for ht, zt in zip(h, zs))
+    s = minimize(cost, [xs[0] >= d[0], xs[1] + zs[0] >= d[1], xs[2] + zs[1] >= d[2],
+                        zs[0] == xs[0] - d[0], zs[1] == xs[1] + zs[0] - d[1],
+                        zs[2] == xs[2] + zs[1] - d[2]])
+    assert (s.objective_value, s[xs[0]], s[xs[1]], s[xs[2]]) == (637.5, 125.0, 0.0, 100.0)
+    x = Var.nonneg()                                                     # test_exceptions.py
+    with pytest.raises(exc.UnboundedError):
+        minimize(-1.0 * x)
+    x, y = Var.nonneg(), Var.nonneg()
+    with pytest.raises(exc.InfeasibleError):
+        minimize(x + y, [x + y == 1, x + y == 2])
