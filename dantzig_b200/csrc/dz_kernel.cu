@@ -511,9 +511,9 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
     // ---- gather: W = dense(B) or dense(B^T), rhs in column M ----------------
     // pre[p] = first flat entry of basis position p; position M is the rhs column.
     {
-        const int total = M * S; // W is 16-byte aligned in both homes
+        const size_t total = (size_t)M * S; // W is 16-byte aligned in both homes
         double2 *W2 = reinterpret_cast<double2 *>(W);
-        for (int e = tid; e < (total >> 1); e += c.nthreads) W2[e] = make_double2(0.0, 0.0);
+        for (size_t e = tid; e < (total >> 1); e += c.nthreads) W2[e] = make_double2(0.0, 0.0);
         if ((total & 1) && tid == 0) W[total - 1] = 0.0;
         for (int i = tid; i < M; i += c.nthreads) {
             c.cnt[i] = 0;
@@ -681,7 +681,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
         // column and reduces it with REDUX ops on the bit pattern of |v| (monotone for
         // non-negative doubles), so no partial results cross warps.
         unsigned bhi = 0u, blo = 0u;
-        int bidx = 0x7fffffff;
+        int bidx = 0x7fffffff, brow = 0;
         // Small M: every warp scans the whole column (no exchange, one barrier less).
         // Large M: warps split the rows and exchange one partial each.
         const bool split = M > 32 * 12;
@@ -713,38 +713,43 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                         hi = 0xffffffffu;
                         lo = 0xffffffffu;
                     }
-                    const int packed = (pos4[q] << 16) | r;
                     const bool better =
                         cand && (bidx == 0x7fffffff || hi > bhi ||
-                                 (hi == bhi && (lo > blo || (lo == blo && packed < bidx))));
+                                 (hi == bhi && (lo > blo || (lo == blo && pos4[q] < bidx))));
                     bhi = better ? hi : bhi;
                     blo = better ? lo : blo;
-                    bidx = better ? packed : bidx;
+                    bidx = better ? pos4[q] : bidx;   // logical position (unique per row)
+                    brow = better ? r : brow;
                 }
             }
         }
         unsigned mh = __reduce_max_sync(kFull, bhi);
         unsigned ml = __reduce_max_sync(kFull, bhi == mh ? blo : 0u);
         int gi = __reduce_min_sync(kFull, (bhi == mh && blo == ml) ? bidx : 0x7fffffff);
+        // the lane that holds the winning position also holds its row
+        int gr = __shfl_sync(kFull, brow, __ffs(__ballot_sync(kFull, bidx == gi)) - 1);
         if (split) {
-            int *rp = c.red_idx + c.parity * 3 * kMaxWarps;
+            int *rp = c.red_idx + c.parity * 4 * kMaxWarps;
             if (lane == 0) {
                 rp[warp] = (int)mh;
                 rp[kMaxWarps + warp] = (int)ml;
                 rp[2 * kMaxWarps + warp] = gi;
+                rp[3 * kMaxWarps + warp] = gr;
             }
             csync(c);
             const bool have = lane < c.nwarps;
             bhi = have ? (unsigned)rp[lane] : 0u;
             blo = have ? (unsigned)rp[kMaxWarps + lane] : 0u;
             bidx = have ? rp[2 * kMaxWarps + lane] : 0x7fffffff;
+            brow = have ? rp[3 * kMaxWarps + lane] : 0;
             if (bidx == 0x7fffffff) bhi = blo = 0u;
             mh = __reduce_max_sync(kFull, bhi);
             ml = __reduce_max_sync(kFull, bhi == mh ? blo : 0u);
             gi = __reduce_min_sync(kFull, (bhi == mh && blo == ml) ? bidx : 0x7fffffff);
+            gr = __shfl_sync(kFull, brow, __ffs(__ballot_sync(kFull, bidx == gi)) - 1);
             c.parity ^= 1;
         }
-        const int pr = gi & 0xffff, ppos = gi >> 16;
+        const int pr = gr, ppos = gi;
         const double pv = W[(size_t)pr * S + k];
         if (c.prof && tid == 0) {
             const long long t = clock64();
@@ -1198,8 +1203,8 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t warps_hint
         *err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
         return DZ_ERR_CUDA;
     }
-    if (M >= 32768) {
-        *err = "batched kernel supports m_int < 32768";
+    if (M >= (1 << 30)) {
+        *err = "kernel supports m_int < 2^30";
         return DZ_ERR_LIMIT;
     }
     const size_t max_smem = prop.sharedMemPerBlockOptin;
