@@ -150,6 +150,11 @@ struct Ctx {
     double *x, *xb, *dxv, *vv, *z, *zb, *dzv;
     double *red_key;
     int *bas, *nb, *rowAt, *posOf, *cnt, *unitRow, *pend, *pre, *red_idx, *ctl;
+    // Large single LPs (HOME == 2): per row of W the half-open column interval
+    // [rlo, rhi) outside of which the row is known to be exactly zero (column M,
+    // the right-hand side, is tracked separately).  W really holds zeros there, so
+    // the intervals only prune loads, zero-fills and loops; they never change values.
+    int *rlo, *rhi;
     int parity;
     // optional phase timing (thread 0 accumulates clock64 deltas into shared memory)
     long long *prof;
@@ -166,6 +171,10 @@ enum {
     PH_RATIO = 6, PH_UPDATE = 7, PH_NONTRIVIAL = 8, PH_PENDING = 9, PH_SOLVES = 10,
     PH_E_SEARCH = 11, PH_E_B2 = 12, PH_E_UPD = 13, PH_E_B1 = 14, PH_COUNT = 16
 };
+
+__device__ __forceinline__ bool in_iv(const Ctx &c, int r, int j) {
+    return !c.rlo || (j >= c.rlo[r] && j < c.rhi[r]);
+}
 
 // Team barrier: the CTA in CTA-per-LP mode, the warp in warp-per-LP mode.
 __device__ __forceinline__ void csync(const Ctx &c) {
@@ -262,17 +271,23 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
             bool has_nz = literal;
             if (!literal) {
                 const double *row = W + (size_t)r * S;
-                for (int j = i + 1; j < M && !has_nz; j += 4) { // four independent loads per trip
+                int jb = i + 1, je = M;
+                if (c.rlo) {
+                    jb = max(jb, c.rlo[r]);
+                    je = min(je, c.rhi[r]);
+                }
+                for (int j = jb; j < je && !has_nz; j += 4) { // four independent loads per trip
                     const double e0 = row[j];
-                    const double e1 = (j + 1 < M) ? row[j + 1] : 0.0;
-                    const double e2 = (j + 2 < M) ? row[j + 2] : 0.0;
-                    const double e3 = (j + 3 < M) ? row[j + 3] : 0.0;
+                    const double e1 = (j + 1 < je) ? row[j + 1] : 0.0;
+                    const double e2 = (j + 2 < je) ? row[j + 2] : 0.0;
+                    const double e3 = (j + 3 < je) ? row[j + 3] : 0.0;
                     has_nz = e0 != 0.0 || e1 != 0.0 || e2 != 0.0 || e3 != 0.0;
                 }
             }
             c.pend[i] = has_nz ? 1 : 0;
             if (!has_nz) {
-                const double di = W[(size_t)r * S + i], bi = W[(size_t)r * S + M];
+                const double di = in_iv(c, r, i) ? W[(size_t)r * S + i] : 0.0;
+                const double bi = W[(size_t)r * S + M];
                 const double yi = (di == 1.0) ? bi : __ddiv_rn(bi, di); // x/1 is the identity
                 y[i] = yi;
                 if (!isfinite(yi)) c.ctl[CTL_FLAG] = 1;
@@ -292,23 +307,29 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
                 pm &= ~(1u << bit);
                 const int i = base + bit;
                 if (c.prof && lane == 0) c.prof[PH_PENDING] += 1;
-                const double *row = W + (size_t)c.rowAt[i] * S;
+                const int rrow = c.rowAt[i];
+                const double *row = W + (size_t)rrow * S;
                 double s = row[M];
-                const double di = row[i];
-                for (int j0 = i + 1; j0 < M; j0 += 128) { // four chunks of loads in flight
+                const double di = in_iv(c, rrow, i) ? row[i] : 0.0;
+                int jb = i + 1, je = M;
+                if (c.rlo && !literal) { // literal mode must see every 0 * y_j (NaN if y_j = inf)
+                    jb = max(jb, c.rlo[rrow]);
+                    je = min(je, c.rhi[rrow]);
+                }
+                for (int j0 = jb; j0 < je; j0 += 128) { // four chunks of loads in flight
                     double u4[4], y4[4];
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         const int j = j0 + lane + 32 * cc;
-                        u4[cc] = (j < M) ? row[j] : 0.0;
-                        y4[cc] = (j < M) ? y[j] : 0.0;
+                        u4[cc] = (j < je) ? row[j] : 0.0;
+                        y4[cc] = (j < je) ? y[j] : 0.0;
                     }
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         const int j = j0 + lane + 32 * cc;
                         const double t = __dmul_rn(u4[cc], y4[cc]);
                         unsigned mk = __ballot_sync(
-                            kFull, literal ? (j < M) : (u4[cc] != 0.0 && y4[cc] != 0.0));
+                            kFull, literal ? (j < je) : (u4[cc] != 0.0 && y4[cc] != 0.0));
                         if (lane == 0) c.n_solve += 2ull * __popc(mk);
                         while (mk) {
                             const int b = __ffs(mk) - 1;
@@ -511,10 +532,26 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
     // ---- gather: W = dense(B) or dense(B^T), rhs in column M ----------------
     // pre[p] = first flat entry of basis position p; position M is the rhs column.
     {
-        const size_t total = (size_t)M * S; // W is 16-byte aligned in both homes
-        double2 *W2 = reinterpret_cast<double2 *>(W);
-        for (size_t e = tid; e < (total >> 1); e += c.nthreads) W2[e] = make_double2(0.0, 0.0);
-        if ((total & 1) && tid == 0) W[total - 1] = 0.0;
+        if (c.rlo) {
+            // only the columns the previous solve may have made nonzero, row by row
+            for (int r = warp; r < M; r += c.nwarps) {
+                const int lo = c.rlo[r], hi = c.rhi[r];
+                double *row = W + (size_t)r * S;
+                if (lo < hi)
+                    for (int j = lo + lane; j < hi; j += 32) row[j] = 0.0;
+                __syncwarp();
+                if (lane == 0) {
+                    row[M] = 0.0;
+                    c.rlo[r] = 0x7fffffff;
+                    c.rhi[r] = 0;
+                }
+            }
+        } else {
+            const size_t total = (size_t)M * S; // W is 16-byte aligned in both homes
+            double2 *W2 = reinterpret_cast<double2 *>(W);
+            for (size_t e = tid; e < (total >> 1); e += c.nthreads) W2[e] = make_double2(0.0, 0.0);
+            if ((total & 1) && tid == 0) W[total - 1] = 0.0;
+        }
         for (int i = tid; i < M; i += c.nthreads) {
             c.cnt[i] = 0;
             c.unitRow[i] = -1;
@@ -609,6 +646,10 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                     W[(size_t)wr * S + wc] = val[q];
                     atomicAdd(&c.cnt[wc], 1);
                     c.unitRow[wc] = wr; // meaningful only where cnt ends at 1
+                    if (c.rlo) {
+                        atomicMin(&c.rlo[wr], wc);
+                        atomicMax(&c.rhi[wr], wc + 1);
+                    }
                 }
             }
         }
@@ -700,7 +741,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int r = rb + q * rstep;
-                    v4[q] = (pos4[q] >= k) ? W[(size_t)r * S + k] : 0.0;
+                    v4[q] = (pos4[q] >= k && in_iv(c, r, k)) ? W[(size_t)r * S + k] : 0.0;
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -750,7 +791,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             c.parity ^= 1;
         }
         const int pr = gr, ppos = gi;
-        const double pv = W[(size_t)pr * S + k];
+        const double pv = in_iv(c, pr, k) ? W[(size_t)pr * S + k] : 0.0;
         if (c.prof && tid == 0) {
             const long long t = clock64();
             c.prof[PH_E_SEARCH] += t - tq;
@@ -778,11 +819,19 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             // four rows in flight.
             const int G = c.G;
             const double *__restrict__ prow = W + (size_t)pr * S;
+            // columns of the pivot row that can be nonzero: (k, M) clipped to its
+            // interval when intervals are tracked, plus the right-hand side column M
+            int jlo = k + 1, jhi = M;
+            if (c.rlo) {
+                jlo = max(jlo, c.rlo[pr]);
+                jhi = min(jhi, c.rhi[pr]);
+            }
+            const double urhs = prow[M];
             for (int rbase = 0; rbase * G < M; rbase += 32) {
                 const int r_own = (rbase + lane) * G + warp;
                 bool need = false;
                 double l = 0.0;
-                if (r_own < M && r_own != pr && c.posOf[r_own] >= k) {
+                if (r_own < M && r_own != pr && c.posOf[r_own] >= k && in_iv(c, r_own, k)) {
                     const double v = W[(size_t)r_own * S + k];
                     if (v != 0.0) {
                         need = true;
@@ -792,14 +841,25 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                 const unsigned rows = __ballot_sync(kFull, need);
                 if (!rows) continue;
                 unsigned long long upd = need ? 1 : 0;
+                if (need) {
+                    if (urhs != 0.0) { // the right-hand side rides along (forward substitution)
+                        double *rp = W + (size_t)r_own * S + M;
+                        *rp = __dsub_rn(*rp, __dmul_rn(l, urhs));
+                        upd += 2;
+                    }
+                    if (c.rlo && jlo < jhi) { // the row may now be nonzero wherever the pivot row is
+                        c.rlo[r_own] = min(c.rlo[r_own], jlo);
+                        c.rhi[r_own] = max(c.rhi[r_own], jhi);
+                    }
+                }
                 // the pivot row four chunks (128 columns) at a time, each batch of loads
                 // independent; two rows of this warp in flight per batch
-                for (int c0 = k + 1; c0 <= M; c0 += 128) {
+                for (int c0 = jlo; c0 < jhi; c0 += 128) {
                     double u[4];
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         const int j = c0 + lane + 32 * cc;
-                        u[cc] = (j <= M) ? prow[j] : 0.0;
+                        u[cc] = (j < jhi) ? prow[j] : 0.0;
                     }
                     unsigned nzu = 0;
 #pragma unroll
@@ -946,6 +1006,12 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
         c.unitRow = ip, ip += M;
         c.pend = ip, ip += M;
         c.pre = ip, ip += M + 2;
+        if (HOME == 2) {
+            c.rlo = ip, ip += M;
+            c.rhi = ip, ip += M;
+        } else {
+            c.rlo = c.rhi = nullptr;
+        }
     }
     const long long max_pivots = Bt.max_pivots;
 
@@ -963,6 +1029,16 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
             c.t_last = clock64();
         }
 
+        if (c.rlo) { // interval mode: W starts all-zero once per LP, every interval empty
+            const size_t total = (size_t)M * c.S;
+            double2 *W2 = reinterpret_cast<double2 *>(c.W);
+            for (size_t e = tid; e < (total >> 1); e += c.nthreads) W2[e] = make_double2(0.0, 0.0);
+            if ((total & 1) && tid == 0) c.W[total - 1] = 0.0;
+            for (int r = tid; r < M; r += c.nthreads) {
+                c.rlo[r] = 0x7fffffff;
+                c.rhi[r] = 0;
+            }
+        }
         // initial state (simplex.rs:190-205)
         for (int p = tid; p < M; p += c.nthreads) {
             c.bas[p] = T.basis0[p];
@@ -1171,6 +1247,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
 
 size_t zvec_bytes_for(int Nn) { return 3 * (size_t)Nn * 8 + ((size_t)Nn + (Nn & 1)) * 4; }
 size_t pvec_bytes_for(int M) { return 4 * (size_t)M * 8 + (7 * (size_t)M + 2) * 4 + 16; }
+size_t iv_bytes_for(int M) { return 2 * (size_t)M * 4; }
 size_t vec_bytes_for(int M, int Nn) { return zvec_bytes_for(Nn) + pvec_bytes_for(M); }
 size_t fixed_smem_bytes(bool warp) {
     return warp ? PH_COUNT * 8 + 8 * 4 + 16
@@ -1273,7 +1350,7 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t warps_hint
     plan->block = (g + 1) * 32;
     plan->w_in_smem = home == 0;
     plan->smem_bytes = (int32_t)smem_bytes_for(M, Nn, home);
-    size_t ws = home == 0 ? 0 : w_bytes_for(M) + (home == 2 ? vec_bytes_for(M, Nn) : 0);
+    size_t ws = home == 0 ? 0 : w_bytes_for(M) + (home == 2 ? vec_bytes_for(M, Nn) + iv_bytes_for(M) : 0);
     plan->gws_doubles_per_cta = (int64_t)(((ws + 15) & ~(size_t)15) / 8);
     const int cps_max = std::max(1, std::min((int)(per_sm / ((size_t)plan->smem_bytes + 1024)),
                                              2048 / plan->block));
