@@ -12,10 +12,9 @@ def run(w, **kw):
     b.close()
     return r
 w5 = generate.config5(2368)
-a = run(w5, worker_warps=-1)
-b = run(w5, worker_warps=3, ctas_per_sm=12)
-print("same results:", np.array_equal(a.trace_hash, b.trace_hash), np.array_equal(a.objective, b.objective, equal_nan=True), np.array_equal(a.status, b.status))
-w = generate.mixed_batch(64, 50, 100)   # M = 141 -> NR 5
-t = Template(w.structure); print("mixed_50x100 lowered", t.m)
-a = run(w, worker_warps=-1); b = run(w, worker_warps=3, basis_home=2)
-print("same results:", np.array_equal(a.trace_hash, b.trace_hash), np.array_equal(a.status, b.status))
+a = run(w5)
+b = run(w5, worker_warps=-1)
+print("same:", np.array_equal(a.trace_hash, b.trace_hash))
+run(generate.config1(range(1)))
+run(generate.config1(range(8)))
+run(generate.config2(4096), worker_warps=3)
