@@ -663,14 +663,26 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
     const bool is_ctl = c.wm ? (tid == 0) : (tid == c.NWK);
     long long tb1 = (c.prof && tid == 0) ? clock64() : 0;
     for (;;) {
-        if (is_ctl) { // retire virgin-unit / empty columns: pure bookkeeping
-            while (k < M - 1) {
-                const int cn = c.cnt[k];
-                if (cn == 0) { // all-zero column: mu = k, pivot 0, nothing moves (linalg.rs:117)
-                    ++k;
-                    continue;
+        if (c.wm || tid >= c.NWK) { // control warp: retire virgin-unit / empty columns
+            // Pure bookkeeping, strictly sequential in general -- but a step whose unit
+            // row already sits at position k (or whose column is empty) changes nothing,
+            // so a run of such steps is checked 32 at a time against the current tables.
+            const int cl = c.wm ? tid : tid - c.NWK;
+            for (;;) {
+                const int kk = k + cl;
+                bool noop = false;
+                if (kk < M - 1) {
+                    const int cn = c.cnt[kk];
+                    noop = cn == 0 || (cn == 1 && c.unitRow[kk] == c.rowAt[kk]);
                 }
-                if (cn == 1) {
+                const unsigned m = __ballot_sync(kFull, noop);
+                const int run = (m == kFull) ? 32 : __ffs(~m) - 1;
+                k += run;
+                if (run == 32) continue;
+                if (k >= M - 1) break;
+                // step k is not a no-op: a real virgin-unit interchange, or a non-trivial step
+                int adv = 0;
+                if (cl == 0 && c.cnt[k] == 1) {
                     const int ur = c.unitRow[k];
                     const int mu = c.posOf[ur];
                     if (mu >= k) { // its row is still active: no fill has reached this column
@@ -679,13 +691,15 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                         c.rowAt[mu] = rk;
                         c.posOf[ur] = k;
                         c.posOf[rk] = mu;
-                        ++k;
-                        continue;
+                        adv = 1;
                     }
                 }
-                break;
+                adv = __shfl_sync(kFull, adv, 0);
+                if (!adv) break;
+                ++k;
+                __syncwarp();
             }
-            c.ctl[CTL_K] = k;
+            if (cl == 0) c.ctl[CTL_K] = k;
         }
         csync(c); // B1: updates of the previous step and the position tables are visible
         k = c.ctl[CTL_K];
