@@ -155,6 +155,8 @@ struct Ctx {
     // the right-hand side, is tracked separately).  W really holds zeros there, so
     // the intervals only prune loads, zero-fills and loops; they never change values.
     int *rlo, *rhi;
+    double *pbuf; // [M + 32 * kMaxWarps] ordered nonzero products of one back-substitution row
+    int *plist;   // [M] pending back-substitution rows, descending position
     int parity;
     // optional phase timing (thread 0 accumulates clock64 deltas into shared memory)
     long long *prof;
@@ -297,6 +299,89 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
     }
     csync(c);
     tick(c, PH_BACK_A);
+    if (c.pbuf) {
+        // Large single LP: the products u_ij * y_j of one row are formed by ALL warps
+        // (each warp a contiguous column segment, compacted in order), then the control
+        // warp runs the strictly sequential subtraction chain over the nonzero products
+        // (linalg.rs:294: j ascending).  Rows still go one after the other, M-1..0.
+        const int lane = tid & 31, warp = tid >> 5, nw = c.nwarps;
+        int *wcnt = c.red_idx; // [kMaxWarps] per-warp product counts
+        if (tid >= c.NWK) { // control warp: pending rows, descending, into plist
+            int n = 0;
+            const int cl = tid - c.NWK;
+            for (int base = (M - 1) & ~31; base >= 0; base -= 32) {
+                const int il = base + 31 - cl; // lane 0 takes the highest position
+                const unsigned pm = __ballot_sync(kFull, il < M && c.pend[il] != 0);
+                if (il < M && c.pend[il] != 0) c.plist[n + __popc(pm & ((1u << cl) - 1u))] = il;
+                n += __popc(pm);
+            }
+            if (cl == 0) c.ctl[CTL_K] = n;
+        }
+        csync(c);
+        const int np = c.ctl[CTL_K];
+        for (int e = 0; e < np; ++e) {
+            const int i = c.plist[e];
+            const int rrow = c.rowAt[i];
+            const double *row = W + (size_t)rrow * S;
+            int jb = i + 1, je = M;
+            if (c.rlo && !literal) { // literal mode must see every 0 * y_j (NaN if y_j = inf)
+                jb = max(jb, c.rlo[rrow]);
+                je = min(je, c.rhi[rrow]);
+            }
+            const int width = max(je - jb, 0);
+            const int seg = (((width + nw - 1) / nw) + 31) & ~31; // columns per warp, multiple of 32
+            {
+                const int s0 = jb + warp * seg, s1 = min(s0 + seg, je);
+                int n = 0;
+                for (int j0 = s0; j0 < s1; j0 += 128) { // four chunks of loads in flight
+                    double u4[4], y4[4];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int j = j0 + lane + 32 * cc;
+                        u4[cc] = (j < s1) ? row[j] : 0.0;
+                        y4[cc] = (j < s1) ? y[j] : 0.0;
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int j = j0 + lane + 32 * cc;
+                        const bool on = literal ? (j < s1) : (u4[cc] != 0.0 && y4[cc] != 0.0);
+                        const unsigned mk = __ballot_sync(kFull, on);
+                        if (on)
+                            c.pbuf[warp * seg + n + __popc(mk & ((1u << lane) - 1u))] =
+                                __dmul_rn(u4[cc], y4[cc]);
+                        n += __popc(mk);
+                    }
+                }
+                if (lane == 0) wcnt[warp] = n;
+            }
+            csync(c);
+            if (tid >= c.NWK) { // control warp: the sequential chain
+                const int cl = tid - c.NWK;
+                double s = row[M];
+                const double di = in_iv(c, rrow, i) ? row[i] : 0.0;
+                unsigned long long ops = 0;
+                for (int w = 0; w < nw; ++w) {
+                    const int n = wcnt[w];
+                    for (int off = 0; off < n; off += 32) {
+                        const int m = min(32, n - off);
+                        const double t = (cl < m) ? c.pbuf[w * seg + off + cl] : 0.0;
+                        for (int b = 0; b < m; ++b) s = __dsub_rn(s, __shfl_sync(kFull, t, b));
+                    }
+                    ops += 2ull * n;
+                }
+                const double yi = (di == 1.0) ? s : __ddiv_rn(s, di);
+                if (cl == 0) {
+                    y[i] = yi;
+                    if (!isfinite(yi)) c.ctl[CTL_FLAG] = 1;
+                    c.n_solve += ops + 1;
+                    if (c.prof) c.prof[PH_PENDING] += 1;
+                }
+            }
+            csync(c); // y[i] visible, pbuf / wcnt free
+        }
+        tick(c, PH_BACK_B);
+        return;
+    }
     if (c.wm || tid >= c.NWK) { // control warp (the warp itself in warp mode)
         const int lane = c.wm ? tid : tid - c.NWK;
         for (int base = (M - 1) & ~31; base >= 0; base -= 32) {
@@ -1023,8 +1108,11 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
         if (HOME == 2) {
             c.rlo = ip, ip += M;
             c.rhi = ip, ip += M;
+            c.plist = ip, ip += M; // 10 M + 2 ints so far: the doubles below stay 8-byte aligned
+            c.pbuf = reinterpret_cast<double *>(ip);
         } else {
-            c.rlo = c.rhi = nullptr;
+            c.rlo = c.rhi = c.plist = nullptr;
+            c.pbuf = nullptr;
         }
     }
     const long long max_pivots = Bt.max_pivots;
@@ -1261,7 +1349,9 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
 
 size_t zvec_bytes_for(int Nn) { return 3 * (size_t)Nn * 8 + ((size_t)Nn + (Nn & 1)) * 4; }
 size_t pvec_bytes_for(int M) { return 4 * (size_t)M * 8 + (7 * (size_t)M + 2) * 4 + 16; }
-size_t iv_bytes_for(int M) { return 2 * (size_t)M * 4; }
+size_t iv_bytes_for(int M) { // intervals, pending list, product buffer (HOME == 2)
+    return 2 * (size_t)M * 4 + ((size_t)M + 1) * 4 + ((size_t)M + 32 * kMaxWarps + 64) * 8 + 16;
+}
 size_t vec_bytes_for(int M, int Nn) { return zvec_bytes_for(Nn) + pvec_bytes_for(M); }
 size_t fixed_smem_bytes(bool warp) {
     return warp ? PH_COUNT * 8 + 8 * 4 + 16
