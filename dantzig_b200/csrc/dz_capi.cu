@@ -75,6 +75,7 @@ static int template_on_device(dz_template *t, int device, dz::TemplateDev *view)
     d.view.Nint = h.n_int;
     d.view.Nn = h.n_int - h.m;
     d.view.n_orig = (int32_t)n_orig;
+    d.view.nnz = (int32_t)nnz;
     d.view.c0_ref = h.c0_ref;
     d.view.col_ptr = d.blob + o_cp;
     d.view.row_idx = d.blob + o_ri;
@@ -239,7 +240,8 @@ int dz_batch_create(const dz_template *tc, int64_t B, const dz_options *opt, dz_
     rc = template_on_device(t, b->opt.device, &b->tview);
     if (rc != DZ_OK) return fail(rc);
     const dz::Template &h = t->host;
-    rc = dz::plan_launch(b->opt.device, h.m, h.n_int - h.m, B, b->opt.worker_warps,
+    rc = dz::plan_launch(b->opt.device, h.m, h.n_int - h.m, (int64_t)h.row_idx.size(), B,
+                         b->opt.worker_warps,
                          b->opt.ctas_per_sm, b->opt.basis_home, &b->plan, &g_err);
     if (rc != DZ_OK) return fail(rc);
     if (b->opt.stream) {

@@ -30,6 +30,7 @@ int pack_theta(const Template *t, const dz_model *m, double *theta, std::string 
 // Device view of a template: plain pointers into one device allocation.
 struct TemplateDev {
     int32_t M, Nint, Nn, n_orig;
+    int32_t nnz;
     int32_t c0_ref;
     const int32_t *col_ptr;   // [Nint+1]
     const int32_t *row_idx;   // [nnz]
@@ -75,8 +76,8 @@ struct LaunchPlan {
     int64_t gws_doubles_per_cta = 0;
 };
 
-int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t warps_hint, int32_t cps_hint,
-                int32_t basis_home, LaunchPlan *plan, std::string *err);
+int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32_t warps_hint,
+                int32_t cps_hint, int32_t basis_home, LaunchPlan *plan, std::string *err);
 // Enqueue the batched solve on `stream` (cudaStream_t passed as void*).
 int launch_batch(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan, void *stream,
                  std::string *err);

@@ -157,6 +157,7 @@ struct Ctx {
     int *rlo, *rhi;
     double *pbuf; // [M + 32 * kMaxWarps] ordered nonzero products of one back-substitution row
     int *plist;   // [M] pending back-substitution rows, descending position
+    double *lval; // [nnz] this LP's lowered values, resolved once from theta (HOME == 2)
     int parity;
     // optional phase timing (thread 0 accumulates clock64 deltas into shared memory)
     long long *prof;
@@ -720,7 +721,8 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             }
             double val[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) val[q] = load_ref(theta, ref[q]);
+            for (int q = 0; q < 4; ++q)
+                val[q] = (c.lval && pp[q] >= 0) ? c.lval[ee[q]] : load_ref(theta, ref[q]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (pp[q] < 0 || val[q] == 0.0) continue;
@@ -1110,9 +1112,10 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
             c.rhi = ip, ip += M;
             c.plist = ip, ip += M; // 10 M + 2 ints so far: the doubles below stay 8-byte aligned
             c.pbuf = reinterpret_cast<double *>(ip);
+            c.lval = c.pbuf + (M + 32 * kMaxWarps + 64);
         } else {
             c.rlo = c.rhi = c.plist = nullptr;
-            c.pbuf = nullptr;
+            c.pbuf = c.lval = nullptr;
         }
     }
     const long long max_pivots = Bt.max_pivots;
@@ -1131,6 +1134,9 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
             c.t_last = clock64();
         }
 
+        if (c.lval) { // resolve the lowered values once: pricing and gathers then stream them
+            for (int e = tid; e < T.nnz; e += c.nthreads) c.lval[e] = load_ref(theta, T.val_ref[e]);
+        }
         if (c.rlo) { // interval mode: W starts all-zero once per LP, every interval empty
             const size_t total = (size_t)M * c.S;
             double2 *W2 = reinterpret_cast<double2 *>(c.W);
@@ -1211,7 +1217,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
                         unsigned cntp = 0;
 #pragma unroll 4
                         for (int e = e0; e < e1; ++e) {
-                            const double a = load_ref(theta, T.val_ref[e]);
+                            const double a = c.lval ? c.lval[e] : load_ref(theta, T.val_ref[e]);
                             const double t = __dadd_rn(s, __dmul_rn(a, -c.vv[T.row_idx[e]]));
                             const bool nz = (a != 0.0);
                             s = nz ? t : s;
@@ -1376,8 +1382,8 @@ cudaError_t launch_one(const TemplateDev &T, const BatchDev &Bt, const LaunchPla
 
 } // namespace
 
-int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t warps_hint, int32_t cps_hint,
-                int32_t basis_home, LaunchPlan *plan, std::string *err) {
+int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32_t warps_hint,
+                int32_t cps_hint, int32_t basis_home, LaunchPlan *plan, std::string *err) {
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) {
@@ -1454,7 +1460,10 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t B, int32_t warps_hint
     plan->block = (g + 1) * 32;
     plan->w_in_smem = home == 0;
     plan->smem_bytes = (int32_t)smem_bytes_for(M, Nn, home);
-    size_t ws = home == 0 ? 0 : w_bytes_for(M) + (home == 2 ? vec_bytes_for(M, Nn) + iv_bytes_for(M) : 0);
+    size_t ws = home == 0 ? 0
+                          : w_bytes_for(M) + (home == 2 ? vec_bytes_for(M, Nn) + iv_bytes_for(M) +
+                                                              (size_t)nnz * 8 + 16
+                                                        : 0);
     plan->gws_doubles_per_cta = (int64_t)(((ws + 15) & ~(size_t)15) / 8);
     const int cps_max = std::max(1, std::min((int)(per_sm / ((size_t)plan->smem_bytes + 1024)),
                                              2048 / plan->block));
