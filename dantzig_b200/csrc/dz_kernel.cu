@@ -158,6 +158,8 @@ struct Ctx {
     double *pbuf; // [M + 32 * kMaxWarps] ordered nonzero products of one back-substitution row
     int *plist;   // [M] pending back-substitution rows, descending position
     double *lval; // [nnz] this LP's lowered values, resolved once from theta (HOME == 2)
+    int *cand_r;  // [M] rows with a nonzero in the current pivot column (found by the search)
+    double *cand_v; // [M] ... and their values
     int parity;
     // optional phase timing (thread 0 accumulates clock64 deltas into shared memory)
     long long *prof;
@@ -166,7 +168,7 @@ struct Ctx {
     unsigned long long n_lu, n_solve, n_price;
 };
 
-enum { CTL_K = 0, CTL_FLAG = 1, CTL_LP = 2, CTL_RHS0 = 3 };
+enum { CTL_K = 0, CTL_FLAG = 1, CTL_LP = 2, CTL_RHS0 = 3, CTL_NC = 4 };
 
 // Phase slots of the optional per-LP cycle profile (BatchDev::prof).
 enum {
@@ -209,7 +211,7 @@ __device__ __forceinline__ void find_first_both(Ctx &c, int &q0, int &p0) {
     for (int k = c.tid; k < c.Nn; k += c.nthreads) {
         const double yb = c.zb[k];
         if (yb > 0.0) {
-            const double ratio = __ddiv_rn(-c.z[k], yb);
+            const double ratio = (yb == 1.0) ? -c.z[k] : __ddiv_rn(-c.z[k], yb); // x/1 == x
             if (ratio == ratio && beats(ratio, k, cd.key[0], cd.idx[0])) {
                 cd.key[0] = ratio;
                 cd.idx[0] = k;
@@ -220,7 +222,7 @@ __device__ __forceinline__ void find_first_both(Ctx &c, int &q0, int &p0) {
     for (int k = c.tid; k < c.M; k += c.nthreads) {
         const double yb = c.xb[k];
         if (yb > 0.0) {
-            const double ratio = __ddiv_rn(-c.x[k], yb);
+            const double ratio = (yb == 1.0) ? -c.x[k] : __ddiv_rn(-c.x[k], yb);
             if (ratio == ratio && beats(ratio, k, cd.key[2], cd.idx[2])) {
                 cd.key[2] = ratio;
                 cd.idx[2] = k;
@@ -786,7 +788,10 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                 ++k;
                 __syncwarp();
             }
-            if (cl == 0) c.ctl[CTL_K] = k;
+            if (cl == 0) {
+                c.ctl[CTL_K] = k;
+                c.ctl[CTL_NC] = 0;
+            }
         }
         csync(c); // B1: updates of the previous step and the position tables are visible
         k = c.ctl[CTL_K];
@@ -827,6 +832,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
         // Small M: every warp scans the whole column (no exchange, one barrier less).
         // Large M: warps split the rows and exchange one partial each.
         const bool split = M > 32 * 12;
+        const bool listed = split && c.cand_r != nullptr;
         {
             // four rows per thread in flight: positions first, then the predicated
             // column loads as one batch of independent loads
@@ -862,6 +868,11 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                     blo = better ? lo : blo;
                     bidx = better ? pos4[q] : bidx;   // logical position (unique per row)
                     brow = better ? r : brow;
+                    if (listed && pos4[q] >= k && v4[q] != 0.0) { // rows the update has to visit
+                        const int e = atomicAdd(&c.ctl[CTL_NC], 1);
+                        c.cand_r[e] = r;
+                        c.cand_v[e] = v4[q];
+                    }
                 }
             }
         }
@@ -928,15 +939,28 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                 jhi = min(jhi, c.rhi[pr]);
             }
             const double urhs = prow[M];
-            for (int rbase = 0; rbase * G < M; rbase += 32) {
-                const int r_own = (rbase + lane) * G + warp;
+            const int nslots = listed ? c.ctl[CTL_NC] : M;
+            for (int rbase = 0; listed ? (rbase < nslots) : (rbase * G < M); rbase += listed ? 32 * G : 32) {
+                // the rows this warp updates: from the search's candidate list when there
+                // is one (no second scan of the column), else the rows it owns
+                int r_own;
                 bool need = false;
                 double l = 0.0;
-                if (r_own < M && r_own != pr && c.posOf[r_own] >= k && in_iv(c, r_own, k)) {
-                    const double v = W[(size_t)r_own * S + k];
-                    if (v != 0.0) {
+                if (listed) {
+                    const int e = rbase + warp * 32 + lane;
+                    r_own = (e < nslots) ? c.cand_r[e] : pr;
+                    if (e < nslots && r_own != pr) {
                         need = true;
-                        l = __ddiv_rn(v, pv);
+                        l = __ddiv_rn(c.cand_v[e], pv);
+                    }
+                } else {
+                    r_own = (rbase + lane) * G + warp;
+                    if (r_own < M && r_own != pr && c.posOf[r_own] >= k && in_iv(c, r_own, k)) {
+                        const double v = W[(size_t)r_own * S + k];
+                        if (v != 0.0) {
+                            need = true;
+                            l = __ddiv_rn(v, pv);
+                        }
                     }
                 }
                 const unsigned rows = __ballot_sync(kFull, need);
@@ -975,8 +999,9 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                         if (two) rr &= rr - 1;
                         const double l0 = __shfl_sync(kFull, l, b0);
                         const double l1 = __shfl_sync(kFull, l, b1);
-                        double *__restrict__ w0 = W + (size_t)((rbase + b0) * G + warp) * S + c0 + lane;
-                        double *__restrict__ w1 = W + (size_t)((rbase + b1) * G + warp) * S + c0 + lane;
+                        const int ra = __shfl_sync(kFull, r_own, b0), rb2 = __shfl_sync(kFull, r_own, b1);
+                        double *__restrict__ w0 = W + (size_t)ra * S + c0 + lane;
+                        double *__restrict__ w1 = W + (size_t)rb2 * S + c0 + lane;
                         double a0[4], a1[4];
 #pragma unroll
                         for (int cc = 0; cc < 4; ++cc) {
@@ -1110,12 +1135,14 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
         if (HOME == 2) {
             c.rlo = ip, ip += M;
             c.rhi = ip, ip += M;
-            c.plist = ip, ip += M; // 10 M + 2 ints so far: the doubles below stay 8-byte aligned
+            c.plist = ip, ip += M;
+            c.cand_r = ip, ip += M + (M & 1); // 11 M + 2 (+1) ints: the doubles below stay aligned
             c.pbuf = reinterpret_cast<double *>(ip);
-            c.lval = c.pbuf + (M + 32 * kMaxWarps + 64);
+            c.cand_v = c.pbuf + (M + 32 * kMaxWarps + 64);
+            c.lval = c.cand_v + M;
         } else {
-            c.rlo = c.rhi = c.plist = nullptr;
-            c.pbuf = c.lval = nullptr;
+            c.rlo = c.rhi = c.plist = c.cand_r = nullptr;
+            c.pbuf = c.lval = c.cand_v = nullptr;
         }
     }
     const long long max_pivots = Bt.max_pivots;
@@ -1356,7 +1383,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
 size_t zvec_bytes_for(int Nn) { return 3 * (size_t)Nn * 8 + ((size_t)Nn + (Nn & 1)) * 4; }
 size_t pvec_bytes_for(int M) { return 4 * (size_t)M * 8 + (7 * (size_t)M + 2) * 4 + 16; }
 size_t iv_bytes_for(int M) { // intervals, pending list, product buffer (HOME == 2)
-    return 2 * (size_t)M * 4 + ((size_t)M + 1) * 4 + ((size_t)M + 32 * kMaxWarps + 64) * 8 + 16;
+    return 2 * (size_t)M * 4 + 2 * ((size_t)M + 1) * 4 + (2 * (size_t)M + 32 * kMaxWarps + 64) * 8 + 16;
 }
 size_t vec_bytes_for(int M, int Nn) { return zvec_bytes_for(Nn) + pvec_bytes_for(M); }
 size_t fixed_smem_bytes(bool warp) {
