@@ -354,6 +354,11 @@ int dz_batch_solve(dz_batch *b) {
     DZ_CUDA(cudaMemsetAsync(b->d_out + b->off_work, 0, sizeof(double) * (size_t)b->B * 4,
                             b->stream));
     DZ_CUDA(cudaEventRecord(b->ev0, b->stream));
+    if (b->plan.home == 2) // interval mode expects an all-zero working basis (see dz_kernel.cu);
+                           // inside the timed region on purpose
+        DZ_CUDA(cudaMemsetAsync(b->d_gws, 0,
+                                sizeof(double) * (size_t)b->plan.gws_doubles_per_cta *
+                                    (size_t)b->plan.teams, b->stream));
     int rc = dz::launch_batch(b->tview, b->bd, b->plan, b->stream, &g_err);
     if (rc != DZ_OK) return rc;
     DZ_CUDA(cudaEventRecord(b->ev1, b->stream));

@@ -181,6 +181,24 @@ __device__ __forceinline__ bool in_iv(const Ctx &c, int r, int j) {
     return !c.rlo || (j >= c.rlo[r] && j < c.rhi[r]);
 }
 
+// Interval mode: zero exactly the columns a solve may have made nonzero, row by row,
+// and reset the intervals; afterwards W is all-zero again (column M included).
+__device__ __forceinline__ void zero_intervals(Ctx &c) {
+    const int lane = c.tid & 31, warp = c.tid >> 5;
+    for (int r = warp; r < c.M; r += c.nwarps) {
+        const int lo = c.rlo[r], hi = c.rhi[r];
+        double *row = c.W + (size_t)r * c.S;
+        if (lo < hi)
+            for (int j = lo + lane; j < hi; j += 32) row[j] = 0.0;
+        __syncwarp();
+        if (lane == 0) {
+            row[c.M] = 0.0;
+            c.rlo[r] = 0x7fffffff;
+            c.rhi[r] = 0;
+        }
+    }
+}
+
 // Team barrier: the CTA in CTA-per-LP mode, the warp in warp-per-LP mode.
 __device__ __forceinline__ void csync(const Ctx &c) {
     if (c.wm)
@@ -621,19 +639,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
     // pre[p] = first flat entry of basis position p; position M is the rhs column.
     {
         if (c.rlo) {
-            // only the columns the previous solve may have made nonzero, row by row
-            for (int r = warp; r < M; r += c.nwarps) {
-                const int lo = c.rlo[r], hi = c.rhi[r];
-                double *row = W + (size_t)r * S;
-                if (lo < hi)
-                    for (int j = lo + lane; j < hi; j += 32) row[j] = 0.0;
-                __syncwarp();
-                if (lane == 0) {
-                    row[M] = 0.0;
-                    c.rlo[r] = 0x7fffffff;
-                    c.rhi[r] = 0;
-                }
-            }
+            zero_intervals(c); // only what the previous solve may have made nonzero
         } else {
             const size_t total = (size_t)M * S; // W is 16-byte aligned in both homes
             double2 *W2 = reinterpret_cast<double2 *>(W);
@@ -1164,11 +1170,8 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
         if (c.lval) { // resolve the lowered values once: pricing and gathers then stream them
             for (int e = tid; e < T.nnz; e += c.nthreads) c.lval[e] = load_ref(theta, T.val_ref[e]);
         }
-        if (c.rlo) { // interval mode: W starts all-zero once per LP, every interval empty
-            const size_t total = (size_t)M * c.S;
-            double2 *W2 = reinterpret_cast<double2 *>(c.W);
-            for (size_t e = tid; e < (total >> 1); e += c.nthreads) W2[e] = make_double2(0.0, 0.0);
-            if ((total & 1) && tid == 0) c.W[total - 1] = 0.0;
+        if (c.rlo) { // interval mode: W is all-zero here (the host zeroes the workspace before
+                     // the launch, every LP cleans up after itself); every interval empty
             for (int r = tid; r < M; r += c.nthreads) {
                 c.rlo[r] = 0x7fffffff;
                 c.rhi[r] = 0;
@@ -1338,6 +1341,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
 
         // ---- results: objective_value / solution, simplex.rs:345-371 ----
         csync(c);
+        if (c.rlo) zero_intervals(c); // leave W all-zero for the next LP of this team
         if (tid == 0) {
             double obj = 0.0;
             for (int p = 0; p < M; ++p)
