@@ -383,11 +383,15 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
                 unsigned long long ops = 0;
                 for (int w = 0; w < nw; ++w) {
                     const int n = wcnt[w];
-                    for (int off = 0; off < n; off += 32) {
-                        const int m = min(32, n - off);
-                        const double t = (cl < m) ? c.pbuf[w * seg + off + cl] : 0.0;
-                        for (int b = 0; b < m; ++b) s = __dsub_rn(s, __shfl_sync(kFull, t, b));
+                    // every lane walks the same compacted products (uniform, cached loads:
+                    // one line holds 16 of them); the loads run ahead of the DSUB chain
+                    const double *pb = c.pbuf + (size_t)w * seg;
+                    int q = 0;
+                    for (; q + 4 <= n; q += 4) {
+                        const double t0 = pb[q], t1 = pb[q + 1], t2 = pb[q + 2], t3 = pb[q + 3];
+                        s = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(s, t0), t1), t2), t3);
                     }
+                    for (; q < n; ++q) s = __dsub_rn(s, pb[q]);
                     ops += 2ull * n;
                 }
                 const double yi = (di == 1.0) ? s : __ddiv_rn(s, di);
