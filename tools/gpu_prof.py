@@ -25,5 +25,12 @@ def run(w, **kw):
     b.close()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 w = generate.config2(B)
-run(w, worker_warps=-1, ctas_per_sm=8)
-run(w, worker_warps=-1, ctas_per_sm=2)
+if len(sys.argv) > 2 and sys.argv[2] == "auto":
+    run(w)  # the shipped launch shape only
+elif len(sys.argv) > 2 and sys.argv[2] == "load":
+    # same kernel, increasing load: 4 warps on 37 SMs ... the full single wave
+    for b in (148, 1184, 2368, 4096):
+        run(generate.config2(b), worker_warps=-1)
+else:
+    run(w, worker_warps=-1, ctas_per_sm=8)
+    run(w, worker_warps=-1, ctas_per_sm=2)
