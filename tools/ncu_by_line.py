@@ -2,6 +2,8 @@
 
 usage: ncu_by_line.py report.ncu-rep lib.so 'kernel-substring' [top]
 Needs the .so the report was captured from (built with -lineinfo).
+Lines of inlined CUDA headers (shuffles, __ldg ...) are charged to the nearest
+preceding dz_kernel.cu line; a per-function summary follows the per-line table.
 """
 import csv, io, os, re, subprocess, sys, tempfile
 
@@ -31,7 +33,8 @@ for f in os.listdir(tmp):
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
         if m:
-            cur_line = int(m.group(2))
+            if m.group(1).endswith("dz_kernel.cu"):
+                cur_line = int(m.group(2))
             continue
         m = re.match(r"\s*/\*([0-9a-f]{4,6})\*/", ln)
         if m:
@@ -58,3 +61,19 @@ for line, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
     st = " ".join("%s=%.0f%%" % (k.replace("stall_", ""), 100 * v / max(a["samples"], 1)) for k, v in st)
     text = src[line - 1].strip()[:70] if line and line <= len(src) else "?"
     print("%5.1f%% smp %5.1f%% ins  L%-4s %-70s %s" % (100 * a["samples"] / tot_s, 100 * a["instr"] / tot_i, line, text, st))
+
+# per-function summary: a line belongs to the last function header above it
+starts = [(i + 1, m.group(1)) for i, l in enumerate(src)
+          for m in [re.match(r"(?:__device__ __forceinline__|__global__|static __device__)\s+[\w:<> ]*?\b(\w+)\(", l.strip())
+                    or re.match(r"(dz_batch_kernel)\(", l.strip())] if m]
+fagg = {}
+for line, a in agg.items():
+    name = "?"
+    for ln0, nm in starts:
+        if line and ln0 <= line:
+            name = nm
+    f = fagg.setdefault(name, [0, 0])
+    f[0] += a["samples"]; f[1] += a["instr"]
+print("\nby function (inlined into the kernel):")
+for name, (sm, ins) in sorted(fagg.items(), key=lambda kv: -kv[1][0]):
+    print("%5.1f%% smp %5.1f%% ins  %s" % (100 * sm / tot_s, 100 * ins / tot_i, name))
