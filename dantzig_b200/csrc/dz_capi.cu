@@ -77,6 +77,8 @@ static int template_on_device(dz_template *t, int device, dz::TemplateDev *view)
     d.view.n_orig = (int32_t)n_orig;
     d.view.nnz = (int32_t)nnz;
     d.view.c0_ref = h.c0_ref;
+    d.view.S = (h.m + 1) | 1;
+    d.view.pad_ = 0;
     d.view.col_ptr = d.blob + o_cp;
     d.view.row_idx = d.blob + o_ri;
     d.view.val_ref = d.blob + o_vr;

@@ -32,6 +32,8 @@ struct TemplateDev {
     int32_t M, Nint, Nn, n_orig;
     int32_t nnz;
     int32_t c0_ref;
+    int32_t S;                // row stride of the working basis: (M + 1) | 1
+    int32_t pad_;
     const int32_t *col_ptr;   // [Nint+1]
     const int32_t *row_idx;   // [nnz]
     const int32_t *val_ref;   // [nnz]

@@ -592,6 +592,11 @@ __device__ __forceinline__ void warp_step_small(Ctx &c, double *__restrict__ W, 
 #pragma unroll
     for (int cc = 0; cc < NR; ++cc) nzu += (u[cc] != 0.0) ? 1u : 0u;
     unsigned long long upd = 0;
+    unsigned nrows = 0;
+    bool nz[NR];
+#pragma unroll
+    for (int cc = 0; cc < NR; ++cc) nz[cc] = u[cc] != 0.0;
+    double *__restrict__ Wb = W + k + 1 + lane; // row r, chunk cc: Wb[r * S + 32 * cc] (int offsets: M <= 256)
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
         const int r = lane + 32 * i;
@@ -600,32 +605,33 @@ __device__ __forceinline__ void warp_step_small(Ctx &c, double *__restrict__ W, 
         if (!rows) continue;
         const double l = need ? __ddiv_rn(v[i], pv) : 0.0;
         upd += need ? 1 : 0;
+        nrows += __popc(rows);
         while (rows) {
             const int b0 = __ffs(rows) - 1;
             rows &= rows - 1;
-            const int b1 = rows ? __ffs(rows) - 1 : -1;
-            if (rows) rows &= rows - 1;
+            const bool two = rows != 0;
+            const int b1 = two ? __ffs(rows) - 1 : b0;
+            rows &= rows - 1; // no-op when already empty
             const double l0 = __shfl_sync(kFull, l, b0);
-            const double l1 = __shfl_sync(kFull, l, b1 < 0 ? b0 : b1);
-            double *__restrict__ w0 = W + (size_t)(b0 + 32 * i) * S + k + 1 + lane;
-            double *__restrict__ w1 = W + (size_t)((b1 < 0 ? b0 : b1) + 32 * i) * S + k + 1 + lane;
-            const bool two = b1 >= 0;
+            const double l1 = __shfl_sync(kFull, l, b1);
+            double *__restrict__ w0 = Wb + (unsigned)(b0 + 32 * i) * (unsigned)S;
+            double *__restrict__ w1 = Wb + (unsigned)(b1 + 32 * i) * (unsigned)S;
             double a0[NR], a1[NR];
 #pragma unroll
             for (int cc = 0; cc < NR; ++cc) {
-                a0[cc] = (u[cc] != 0.0) ? w0[32 * cc] : 0.0;
-                a1[cc] = (two && u[cc] != 0.0) ? w1[32 * cc] : 0.0;
+                a0[cc] = nz[cc] ? w0[32 * cc] : 0.0;
+                a1[cc] = (two && nz[cc]) ? w1[32 * cc] : 0.0;
             }
 #pragma unroll
             for (int cc = 0; cc < NR; ++cc) {
-                if (u[cc] != 0.0) {
+                if (nz[cc]) {
                     w0[32 * cc] = __dsub_rn(a0[cc], __dmul_rn(l0, u[cc]));
                     if (two) w1[32 * cc] = __dsub_rn(a1[cc], __dmul_rn(l1, u[cc]));
                 }
             }
-            upd += 2ull * nzu * (two ? 2 : 1);
         }
     }
+    upd += 2ull * nzu * nrows;
     c.n_lu += upd;
 }
 
@@ -1078,7 +1084,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
     Ctx c;
     c.M = T.M;
     c.Nn = T.Nn;
-    c.S = (T.M + 1) | 1;
+    c.S = T.S; // (M + 1) | 1, read from the parameter bank wherever it is needed
     c.wm = WARP;
     c.tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
     c.nthreads = WARP ? 32 : (int)blockDim.x;
