@@ -12,6 +12,7 @@
 //   PyInequality(*, linexpr, b)                                   pyobjs.rs:135-152
 //   PySolution                      objective_value, __getitem__ (0.0 for an
 //                                   unknown variable)             pyobjs.rs:154-175
+//   solve_batch(objectives, constraints)  new: one launch per group of equal structure
 //   solve(objective, constraints)   lib.rs:16-27; raises
 //                                   dantzig.exceptions.UnboundedError /
 //                                   InfeasibleError with the reference's text.
@@ -26,6 +27,7 @@
 #include <atomic>
 #include <cstdint>
 #include <optional>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -124,7 +126,7 @@ struct Flat {
     }
 };
 
-Solution solve(const AffExpr &objective, const std::vector<Inequality> &constraints) {
+Flat flatten(const AffExpr &objective, const std::vector<Inequality> &constraints) {
     Flat f;
     const std::size_t n_obj = std::min(objective.linexpr.coefs.size(), objective.linexpr.vars.size());
     for (std::size_t i = 0; i < n_obj; ++i) {
@@ -140,6 +142,10 @@ Solution solve(const AffExpr &objective, const std::vector<Inequality> &constrai
         f.row_ptr.push_back((int64_t)f.row_var.size());
         f.rhs.push_back(c.b);
     }
+    return f;
+}
+
+dz_model model_of(const Flat &f, double obj_const) {
     dz_model m{};
     m.n_vars = (int32_t)f.ids.size();
     m.has_lb = f.has_lb.data();
@@ -149,12 +155,34 @@ Solution solve(const AffExpr &objective, const std::vector<Inequality> &constrai
     m.n_obj = (int32_t)f.obj_var.size();
     m.obj_var = f.obj_var.data();
     m.obj_coef = f.obj_coef.data();
-    m.obj_const = objective.constant;
+    m.obj_const = obj_const;
     m.n_rows = (int32_t)f.rhs.size();
     m.row_ptr = f.row_ptr.data();
     m.row_var = f.row_var.data();
     m.row_coef = f.row_coef.data();
     m.rhs = f.rhs.data();
+    return m;
+}
+
+// What the lowering depends on besides the numbers: the variable table's bound
+// flags and the index pattern of the objective and of every row.  LPs with equal
+// keys share one dz_template.
+std::string structure_key(const Flat &f) {
+    std::string k;
+    auto put = [&k](const void *p, std::size_t n) { k.append(static_cast<const char *>(p), n); };
+    const int64_t head[3] = {(int64_t)f.ids.size(), (int64_t)f.obj_var.size(), (int64_t)f.rhs.size()};
+    put(head, sizeof(head));
+    put(f.has_lb.data(), f.has_lb.size());
+    put(f.has_ub.data(), f.has_ub.size());
+    put(f.obj_var.data(), f.obj_var.size() * sizeof(int32_t));
+    put(f.row_ptr.data(), f.row_ptr.size() * sizeof(int64_t));
+    put(f.row_var.data(), f.row_var.size() * sizeof(int32_t));
+    return k;
+}
+
+Solution solve(const AffExpr &objective, const std::vector<Inequality> &constraints) {
+    const Flat f = flatten(objective, constraints);
+    dz_model m = model_of(f, objective.constant);
 
     dz_options opt;
     dz_options_default(&opt);
@@ -194,6 +222,121 @@ Solution solve(const AffExpr &objective, const std::vector<Inequality> &constrai
     s.trace_hash = sol.trace_hash;
     for (std::size_t k = 0; k < f.ids.size(); ++k) s.values[f.ids[k]] = values[k];
     return s;
+}
+
+// Batched entry (no reference analogue): LP i is
+// (objectives[i], constraints[i]) with solve()'s meaning.  LPs are grouped by
+// structure, each group goes through dz_solve_batch as one launch, and the
+// result list holds, per LP and in input order, a PySolution or the exception
+// instance solve() would have raised (returned, not raised).
+py::list solve_batch(const std::vector<AffExpr> &objectives,
+                     const std::vector<std::vector<Inequality>> &constraints) {
+    if (objectives.size() != constraints.size())
+        throw py::value_error("solve_batch: objectives and constraints differ in length");
+    const std::size_t n = objectives.size();
+    std::vector<Flat> flats;
+    flats.reserve(n);
+    std::vector<std::string> keys;                                   // first-seen order
+    std::unordered_map<std::string, std::vector<std::size_t>> groups;
+    for (std::size_t i = 0; i < n; ++i) {
+        flats.push_back(flatten(objectives[i], constraints[i]));
+        std::string k = structure_key(flats.back());
+        auto it = groups.find(k);
+        if (it == groups.end()) {
+            keys.push_back(k);
+            groups.emplace(std::move(k), std::vector<std::size_t>{i});
+        } else {
+            it->second.push_back(i);
+        }
+    }
+    std::vector<int32_t> status(n, 0), pivots(n, 0);
+    std::vector<uint64_t> hash(n, 0);
+    std::vector<double> objective(n, 0.0);
+    std::vector<std::vector<double>> values(n);
+    std::string failure;
+    {
+        py::gil_scoped_release release;
+        dz_options opt;
+        dz_options_default(&opt);
+        for (const auto &k : keys) {
+            const auto &members = groups[k];
+            const std::size_t B = members.size();
+            dz_template *t = nullptr;
+            dz_model m0 = model_of(flats[members[0]], objectives[members[0]].constant);
+            if (dz_template_create(&m0, &t) != DZ_OK) {
+                failure = dz_last_error();
+                break;
+            }
+            dz_template_info info{};
+            dz_template_get_info(t, &info);
+            std::vector<int32_t> orig((std::size_t)std::max(info.n_orig, 1));
+            dz_template_get_arrays(t, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                   orig.data(), nullptr, nullptr);
+            std::vector<double> theta(B * (std::size_t)info.n_theta);
+            int rc = DZ_OK;
+            for (std::size_t j = 0; j < B && rc == DZ_OK; ++j) {
+                dz_model mj = model_of(flats[members[j]], objectives[members[j]].constant);
+                rc = dz_template_pack_theta(t, &mj, theta.data() + j * (std::size_t)info.n_theta);
+            }
+            std::vector<int32_t> st(B), pv(B), np(B);
+            std::vector<uint64_t> th(B);
+            std::vector<double> ob(B), vals(std::max<std::size_t>(B * (std::size_t)info.n_orig, 1));
+            if (rc == DZ_OK) {
+                dz_batch_result r{};
+                r.status = st.data();
+                r.pivots = pv.data();
+                r.n_primal = np.data();
+                r.trace_hash = th.data();
+                r.objective = ob.data();
+                r.values = vals.data();
+                rc = dz_solve_batch(t, (int64_t)B, theta.data(), &opt, &r);
+            }
+            if (rc != DZ_OK) failure = dz_last_error();
+            dz_template_destroy(t);
+            if (rc != DZ_OK) break;
+            for (std::size_t j = 0; j < B; ++j) {
+                const std::size_t i = members[j];
+                status[i] = st[j];
+                pivots[i] = pv[j];
+                hash[i] = th[j];
+                objective[i] = ob[j];
+                values[i].assign(flats[i].ids.size(), 0.0);
+                for (int32_t o = 0; o < info.n_orig; ++o)
+                    values[i][(std::size_t)orig[(std::size_t)o]] = vals[j * (std::size_t)info.n_orig + (std::size_t)o];
+            }
+        }
+    }
+    if (!failure.empty()) throw std::runtime_error("dantzig_b200: " + failure);
+    py::object exceptions = py::module_::import("dantzig.exceptions");
+    py::object panic = py::module_::import("dantzig.rust").attr("PanicException");
+    py::list out;
+    for (std::size_t i = 0; i < n; ++i) {
+        switch (status[i]) {
+        case DZ_OPTIMAL: {
+            Solution s;
+            s.objective_value = objective[i];
+            s.pivots = pivots[i];
+            s.trace_hash = hash[i];
+            for (std::size_t k = 0; k < flats[i].ids.size(); ++k) s.values[flats[i].ids[k]] = values[i][k];
+            out.append(py::cast(std::move(s)));
+            break;
+        }
+        case DZ_UNBOUNDED:
+            out.append(exceptions.attr("UnboundedError")("The objective is unbounded"));
+            break;
+        case DZ_INFEASIBLE:
+            out.append(exceptions.attr("InfeasibleError")("The model is infeasible"));
+            break;
+        case DZ_BREAKDOWN:
+            out.append(panic("numerical breakdown: the reference solver panics on this model "
+                             "(safe_divide / unexpected code path)"));
+            break;
+        default:
+            out.append(py::module_::import("builtins").attr("RuntimeError")(
+                "dantzig_b200: pivot watchdog reached (the reference would not terminate)"));
+        }
+    }
+    return out;
 }
 
 } // namespace
@@ -240,4 +383,5 @@ PYBIND11_MODULE(rust, m) {
         });
 
     m.def("solve", &solve, py::arg("objective"), py::arg("constraints"));
+    m.def("solve_batch", &solve_batch, py::arg("objectives"), py::arg("constraints"));
 }

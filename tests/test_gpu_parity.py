@@ -339,6 +339,39 @@ def _frontend(rs):
     return bind(rs) + (sys.modules["dantzig.exceptions"],)
 
 
+def test_rust_module_solve_batch():
+    """dantzig.rust.solve_batch: mixed structures and outcomes in one call; every
+    entry equals what solve() returns (or raises) for the same LP, bit for bit."""
+    import dantzig_b200.rust as rs
+
+    _, _, _, exc_mod = _frontend(rs)
+    rng = np.random.default_rng(7)
+    objs, rows = [], []
+    for i in range(24):                                  # three structures, 8 LPs each
+        m, n = [(3, 4), (5, 6), (4, 8)][i % 3]
+        xs = [rs.Variable(lb=0.0, ub=None) for _ in range(n)]
+        A = rng.uniform(0.1, 1.0, (m, n))
+        objs.append(rs.PyAffExpr(linexpr=rs.PyLinExpr(rng.uniform(0.5, 1.5, n).tolist(), xs), constant=float(i)))
+        rows.append([rs.PyInequality(linexpr=rs.PyLinExpr(A[r].tolist(), xs), b=float(n) * 0.25) for r in range(m)])
+    x, y = rs.Variable(lb=0.0, ub=None), rs.Variable(lb=0.0, ub=None)
+    le = rs.PyLinExpr([1.0, 1.0], [x, y])
+    objs.append(rs.PyAffExpr(linexpr=rs.PyLinExpr([1.0], [x]), constant=0.0))       # unbounded
+    rows.append([])
+    objs.append(rs.PyAffExpr(linexpr=le, constant=0.0))                            # infeasible
+    rows.append([rs.PyInequality(linexpr=le, b=1.0), rs.PyInequality(linexpr=-le, b=-1.0),
+                 rs.PyInequality(linexpr=le, b=2.0), rs.PyInequality(linexpr=-le, b=-2.0)])
+    out = rs.solve_batch(objs, rows)
+    assert len(out) == len(objs)
+    assert isinstance(out[-2], exc_mod.UnboundedError) and str(out[-2]) == "The objective is unbounded"
+    assert isinstance(out[-1], exc_mod.InfeasibleError) and str(out[-1]) == "The model is infeasible"
+    for i in range(24):
+        one = rs.solve(objs[i], rows[i])
+        assert isinstance(out[i], rs.PySolution)
+        assert (out[i].pivots, out[i].trace_hash) == (one.pivots, one.trace_hash)
+        assert bits(out[i].objective_value) == bits(one.objective_value)
+    assert rs.solve_batch([], []) == []
+
+
 def test_reference_python_tests_through_the_module():
     """The reference's tests/test_optimize.py and tests/test_exceptions.py, driven
     through the drop-in module with the call sequence the reference frontend makes

@@ -18,7 +18,7 @@ def rs():
 
 def test_surface(rs):
     assert rs.__name__ == "dantzig.rust"
-    for name in ("Variable", "PyLinExpr", "PyAffExpr", "PyInequality", "PySolution", "solve"):
+    for name in ("Variable", "PyLinExpr", "PyAffExpr", "PyInequality", "PySolution", "solve", "solve_batch"):
         assert hasattr(rs, name)
     assert rs.Variable.__module__ == "dantzig.rust"
     with pytest.raises(TypeError):
@@ -40,6 +40,20 @@ def test_linexpr_algebra(rs):
     aff = rs.PyAffExpr(linexpr=ex + ey, constant=5.0)
     assert aff.constant == 5.0 and aff.pylinexpr.map_ids_to_coefs() == {x.id: 1.0, y.id: 1.0}
     rs.PyInequality(linexpr=ex, b=1.0)
+
+
+def test_solve_batch_host_side(rs):
+    """Argument checking, and no CPU fallback: without a GPU the call fails loudly."""
+    from dantzig_b200 import device_count
+
+    x = rs.Variable(lb=0.0, ub=None)
+    obj = rs.PyAffExpr(linexpr=rs.PyLinExpr([1.0], [x]), constant=0.0)
+    row = rs.PyInequality(linexpr=rs.PyLinExpr([1.0], [x]), b=1.0)
+    with pytest.raises(ValueError):
+        rs.solve_batch([obj, obj], [[row]])
+    if device_count() == 0:
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            rs.solve_batch([obj], [[row]])
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
