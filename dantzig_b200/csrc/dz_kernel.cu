@@ -62,6 +62,28 @@
 #include <cstdio>
 #include <cstdlib>
 
+// Build-time variants kept for A/B runs (tools/gpu_ab.py); all default to the shipped code.
+//   DZ_BSUB_COMPACT  warp back-substitution: the nonzero products of a row are compacted into
+//                    shared memory in order and subtracted by a plain load+sub chain instead
+//                    of one ballot-driven shuffle per product
+//   DZ_BSUB_U32      warp back-substitution: 32-bit unsigned row offsets (the trick that paid in
+//                    the warp step)
+//   DZ_OPAQUE_LANE   the lane id of a warp team comes from %laneid through an opaque asm, so it
+//                    stays in a register instead of being rematerialised from %tid in loops
+//   DZ_STEP_PROFILE  with opt.profile, warp_step_small splits its cycles into the PH_E_* slots
+#ifndef DZ_BSUB_COMPACT
+#define DZ_BSUB_COMPACT 0
+#endif
+#ifndef DZ_BSUB_U32
+#define DZ_BSUB_U32 0
+#endif
+#ifndef DZ_OPAQUE_LANE
+#define DZ_OPAQUE_LANE 0
+#endif
+#ifndef DZ_STEP_PROFILE
+#define DZ_STEP_PROFILE 0
+#endif
+
 namespace dz {
 
 namespace {
@@ -157,6 +179,7 @@ struct Ctx {
     int *rlo, *rhi;
     double *pbuf; // [M + 32 * kMaxWarps] ordered nonzero products of one back-substitution row
     int *plist;   // [M] pending back-substitution rows, descending position
+    double *bsbuf; // [M] DZ_BSUB_COMPACT: ordered nonzero products of one back-substitution row
     double *lval; // [nnz] this LP's lowered values, resolved once from theta (HOME == 2)
     int *cand_r;  // [M] rows with a nonzero in the current pivot column (found by the search)
     double *cand_v; // [M] ... and their values
@@ -474,7 +497,11 @@ __device__ __forceinline__ void warp_back_substitute_small(Ctx &c, double *y, co
     const double *__restrict__ W = c.W;
     double uu[NR], nu[NR], d = 0.0, rhs = 0.0, nd = 0.0, nrhs = 0.0;
     {
+#if DZ_BSUB_U32
+        const double *rowp = W + (unsigned)c.rowAt[M - 1] * (unsigned)S;
+#else
         const double *rowp = W + (size_t)c.rowAt[M - 1] * S;
+#endif
 #pragma unroll
         for (int cc = 0; cc < NR; ++cc) nu[cc] = 0.0;
         nd = rowp[M - 1];
@@ -487,7 +514,11 @@ __device__ __forceinline__ void warp_back_substitute_small(Ctx &c, double *y, co
         d = nd;
         rhs = nrhs;
         if (i > 0) { // prefetch row i-1 (its U entries do not depend on y)
+#if DZ_BSUB_U32
+            const double *rowp = W + (unsigned)c.rowAt[i - 1] * (unsigned)S;
+#else
             const double *rowp = W + (size_t)c.rowAt[i - 1] * S;
+#endif
 #pragma unroll
             for (int cc = 0; cc < NR; ++cc) {
                 const int j = i + lane + 32 * cc;
@@ -497,6 +528,23 @@ __device__ __forceinline__ void warp_back_substitute_small(Ctx &c, double *y, co
             nrhs = rowp[M];
         }
         double s = rhs;
+#if DZ_BSUB_COMPACT
+        int cnt = 0;
+#pragma unroll
+        for (int cc = 0; cc < NR; ++cc) {
+            const int j = i + 1 + lane + 32 * cc;
+            if (i + 1 + 32 * cc >= M) break;
+            const double yj = (j < M) ? y[j] : 0.0;
+            const bool take = literal ? (j < M) : (uu[cc] != 0.0 && yj != 0.0);
+            const unsigned mk = __ballot_sync(kFull, take);
+            if (take) c.bsbuf[cnt + __popc(mk & ((1u << lane) - 1u))] = __dmul_rn(uu[cc], yj);
+            cnt += __popc(mk);
+        }
+        __syncwarp();
+        ops += 2ull * (unsigned)cnt;
+#pragma unroll 4
+        for (int q = 0; q < cnt; ++q) s = __dsub_rn(s, c.bsbuf[q]); // ascending column order
+#else
 #pragma unroll
         for (int cc = 0; cc < NR; ++cc) {
             const int j = i + 1 + lane + 32 * cc;
@@ -511,6 +559,7 @@ __device__ __forceinline__ void warp_back_substitute_small(Ctx &c, double *y, co
                 s = __dsub_rn(s, __shfl_sync(kFull, t, b));
             }
         }
+#endif
         const double yi = (d == 1.0) ? s : __ddiv_rn(s, d);
         if (lane == 0) {
             y[i] = yi;
@@ -534,6 +583,17 @@ template <int NR>
 __device__ __forceinline__ void warp_step_small(Ctx &c, double *__restrict__ W, const int k,
                                                 const bool is_ctl) {
     const int M = c.M, S = c.S, lane = c.tid;
+#if DZ_STEP_PROFILE
+    long long tp = (c.prof && lane == 0) ? clock64() : 0;
+#define DZ_STEP_TICK(slot)                                   \
+    if (c.prof && lane == 0) {                               \
+        const long long tn = clock64();                      \
+        c.prof[slot] += tn - tp;                             \
+        tp = tn;                                             \
+    }
+#else
+#define DZ_STEP_TICK(slot)
+#endif
     int pos[NR];
     double v[NR];
 #pragma unroll
@@ -569,6 +629,7 @@ __device__ __forceinline__ void warp_step_small(Ctx &c, double *__restrict__ W, 
     const unsigned ml = __reduce_max_sync(kFull, bhi == mh ? blo : 0u);
     const int gi = __reduce_min_sync(kFull, (bhi == mh && blo == ml) ? bidx : 0x7fffffff);
     const int pr = gi & 0xffff, ppos = gi >> 16;
+    DZ_STEP_TICK(PH_E_SEARCH) // column loads + arg-max
     const double *__restrict__ prow = W + (size_t)pr * S;
     const double pv = prow[k];
     // pivot row, up to four chunks of 32 columns (column M is the right-hand side)
@@ -591,6 +652,7 @@ __device__ __forceinline__ void warp_step_small(Ctx &c, double *__restrict__ W, 
     unsigned nzu = 0;
 #pragma unroll
     for (int cc = 0; cc < NR; ++cc) nzu += (u[cc] != 0.0) ? 1u : 0u;
+    DZ_STEP_TICK(PH_E_B2) // pivot row loads + interchange bookkeeping
     unsigned long long upd = 0;
     unsigned nrows = 0;
     bool nz[NR];
@@ -633,6 +695,8 @@ __device__ __forceinline__ void warp_step_small(Ctx &c, double *__restrict__ W, 
     }
     upd += 2ull * nzu * nrows;
     c.n_lu += upd;
+    DZ_STEP_TICK(PH_E_UPD) // multipliers + row-pair updates
+#undef DZ_STEP_TICK
 }
 
 // lu_solve (linalg.rs:8-10) of B (transposed == false, rhs = column `arg` of A)
@@ -1086,7 +1150,17 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
     c.Nn = T.Nn;
     c.S = T.S; // (M + 1) | 1, read from the parameter bank wherever it is needed
     c.wm = WARP;
+#if DZ_OPAQUE_LANE
+    if (WARP) {
+        unsigned lid;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lid));
+        c.tid = (int)lid;
+    } else {
+        c.tid = (int)threadIdx.x;
+    }
+#else
     c.tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+#endif
     c.nthreads = WARP ? 32 : (int)blockDim.x;
     c.nwarps = WARP ? 1 : (int)(blockDim.x >> 5);
     c.G = WARP ? 1 : c.nwarps - 1;
@@ -1148,6 +1222,14 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
         c.unitRow = ip, ip += M;
         c.pend = ip, ip += M;
         c.pre = ip, ip += M + 2;
+        c.bsbuf = nullptr;
+#if DZ_BSUB_COMPACT
+        if (WARP) {
+            ip += M & 1; // 7 M + 2 ints so far: keep the doubles 8-byte aligned
+            c.bsbuf = reinterpret_cast<double *>(ip);
+            ip += 2 * M;
+        }
+#endif
         if (HOME == 2) {
             c.rlo = ip, ip += M;
             c.rhi = ip, ip += M;
@@ -1455,7 +1537,8 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
     const bool auto_warp = warps_hint == 0 && basis_home == 0 && M <= 128 && B >= (int64_t)sms * 8;
     if ((warps_hint < 0 || auto_warp) && without <= max_smem / 2 && M <= 1024) {
         // warp-per-LP: WPC independent warps per CTA, basis in the HBM workspace
-        const size_t per_team = (fixed_smem_bytes(true) + pvec_bytes_for(M) + 15) & ~(size_t)15;
+        const size_t per_team =
+            (fixed_smem_bytes(true) + pvec_bytes_for(M) + (DZ_BSUB_COMPACT ? 8 * (size_t)M + 8 : 0) + 15) & ~(size_t)15;
         int wpc = (int)std::min<size_t>(4, max_smem / per_team);
         wpc = std::max(1, wpc);
         plan->warp_mode = true;
