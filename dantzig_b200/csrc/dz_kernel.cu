@@ -68,6 +68,8 @@
 //                    of one ballot-driven shuffle per product
 //   DZ_BSUB_U32      warp back-substitution: 32-bit unsigned row offsets (the trick that paid in
 //                    the warp step)
+//   DZ_NOINLINE      warp_step_small / warp_back_substitute_small as real functions, so that the
+//                    register allocator sees each hot loop on its own
 //   DZ_OPAQUE_LANE   the lane id of a warp team comes from %laneid through an opaque asm, so it
 //                    stays in a register instead of being rematerialised from %tid in loops
 //   DZ_STEP_PROFILE  with opt.profile, warp_step_small splits its cycles into the PH_E_* slots
@@ -76,6 +78,14 @@
 #endif
 #ifndef DZ_BSUB_U32
 #define DZ_BSUB_U32 0
+#endif
+#ifndef DZ_NOINLINE
+#define DZ_NOINLINE 0
+#endif
+#if DZ_NOINLINE
+#define DZ_HOT_FN __device__ __noinline__
+#else
+#define DZ_HOT_FN __device__ __forceinline__
 #endif
 #ifndef DZ_OPAQUE_LANE
 #define DZ_OPAQUE_LANE 0
@@ -492,7 +502,7 @@ __device__ __forceinline__ void back_substitute(Ctx &c, double *y, bool literal)
 // Products with an exact-zero factor are skipped unless `literal`; division by an
 // exact 1.0 (every slack pivot) is the identity and is elided.
 template <int NR>
-__device__ __forceinline__ void warp_back_substitute_small(Ctx &c, double *y, const bool literal) {
+DZ_HOT_FN void warp_back_substitute_small(Ctx &c, double *y, const bool literal) {
     const int M = c.M, S = c.S, lane = c.tid;
     const double *__restrict__ W = c.W;
     double uu[NR], nu[NR], d = 0.0, rhs = 0.0, nd = 0.0, nrhs = 0.0;
@@ -580,7 +590,7 @@ __device__ __forceinline__ void warp_back_substitute_small(Ctx &c, double *y, co
 // HBM/L2 workspace, ~0.3-0.8 us away) instead of one dependent load at a time,
 // and the values read by the pivot search are reused for the multipliers.
 template <int NR>
-__device__ __forceinline__ void warp_step_small(Ctx &c, double *__restrict__ W, const int k,
+DZ_HOT_FN void warp_step_small(Ctx &c, double *__restrict__ W, const int k,
                                                 const bool is_ctl) {
     const int M = c.M, S = c.S, lane = c.tid;
 #if DZ_STEP_PROFILE
