@@ -68,6 +68,10 @@
 //                    of one ballot-driven shuffle per product
 //   DZ_BSUB_U32      warp back-substitution: 32-bit unsigned row offsets (the trick that paid in
 //                    the warp step)
+//   DZ_STEP_TILED    warp step update with the lanes tiled over (rows to update) x (nonzero
+//                    columns of the pivot row) instead of 32 consecutive columns: the pivot
+//                    row has a median of 5 nonzeros at config 2, so lanes-on-columns leaves most
+//                    lanes idle and needs one dependent round trip per pair of rows
 //   DZ_NOINLINE      warp_step_small / warp_back_substitute_small as real functions, so that the
 //                    register allocator sees each hot loop on its own
 //   DZ_OPAQUE_LANE   the lane id of a warp team comes from %laneid through an opaque asm, so it
@@ -78,6 +82,9 @@
 #endif
 #ifndef DZ_BSUB_U32
 #define DZ_BSUB_U32 0
+#endif
+#ifndef DZ_STEP_TILED
+#define DZ_STEP_TILED 0
 #endif
 #ifndef DZ_NOINLINE
 #define DZ_NOINLINE 0
@@ -189,6 +196,7 @@ struct Ctx {
     int *rlo, *rhi;
     double *pbuf; // [M + 32 * kMaxWarps] ordered nonzero products of one back-substitution row
     int *plist;   // [M] pending back-substitution rows, descending position
+    int *clist;    // [M + 2] DZ_STEP_TILED: dense indices of the pivot row's nonzero columns
     double *bsbuf; // [M] DZ_BSUB_COMPACT: ordered nonzero products of one back-substitution row
     double *lval; // [nnz] this LP's lowered values, resolved once from theta (HOME == 2)
     int *cand_r;  // [M] rows with a nonzero in the current pivot column (found by the search)
@@ -590,8 +598,8 @@ DZ_HOT_FN void warp_back_substitute_small(Ctx &c, double *y, const bool literal)
 // HBM/L2 workspace, ~0.3-0.8 us away) instead of one dependent load at a time,
 // and the values read by the pivot search are reused for the multipliers.
 template <int NR>
-DZ_HOT_FN void warp_step_small(Ctx &c, double *__restrict__ W, const int k,
-                                                const bool is_ctl) {
+DZ_HOT_FN void warp_step_small(Ctx &c, double *__restrict__ W, const int k, const bool is_ctl,
+                               double *__restrict__ scratch) {
     const int M = c.M, S = c.S, lane = c.tid;
 #if DZ_STEP_PROFILE
     long long tp = (c.prof && lane == 0) ? clock64() : 0;
@@ -664,6 +672,81 @@ DZ_HOT_FN void warp_step_small(Ctx &c, double *__restrict__ W, const int k,
     for (int cc = 0; cc < NR; ++cc) nzu += (u[cc] != 0.0) ? 1u : 0u;
     DZ_STEP_TICK(PH_E_B2) // pivot row loads + interchange bookkeeping
     unsigned long long upd = 0;
+#if DZ_STEP_TILED
+    if constexpr (NR <= 4) {
+        // Three per-warp lists in shared memory: the pivot row's nonzero columns (clist),
+        // the rows to update and their multipliers (`pre` is idle outside the gather, this
+        // solve's output vector `scratch` until the back-substitution).  The 32 lanes then
+        // tile the nR x nC block of elements to update, four rows in flight per lane: the
+        // same elements get the same two operations as in the row-pair loop below.
+        const unsigned lt = (1u << lane) - 1u;
+        int *__restrict__ clist = c.clist;
+        int *__restrict__ rlist = c.pre;
+        int nC = 0, nR = 0;
+#pragma unroll
+        for (int cc = 0; cc < NR; ++cc) {
+            const bool nzc = u[cc] != 0.0;
+            const unsigned mk = __ballot_sync(kFull, nzc);
+            if (nzc) clist[nC + __popc(mk & lt)] = lane + 32 * cc;
+            nC += __popc(mk);
+        }
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int r = lane + 32 * i;
+            const bool need = pos[i] >= k && r != pr && v[i] != 0.0;
+            const unsigned mk = __ballot_sync(kFull, need);
+            if (need) {
+                const int t = nR + __popc(mk & lt);
+                rlist[t] = r;
+                scratch[t] = __ddiv_rn(v[i], pv);
+            }
+            nR += __popc(mk);
+            upd += need ? 1 : 0;
+        }
+        __syncwarp();
+        if (nR > 0 && nC > 0) {
+            const int lgc = nC <= 4 ? 2 : (nC <= 8 ? 3 : (nC <= 16 ? 4 : 5));
+            const int LC = 1 << lgc, LR = 32 >> lgc;
+            const int lc = lane & (LC - 1), lr = lane >> lgc;
+            for (int cb = 0; cb < nC; cb += LC) { // warp-uniform: the shuffles below need every lane
+                const bool cact = cb + lc < nC;
+                const int d = cact ? clist[cb + lc] : 0; // column k + 1 + d; its value sits in lane d % 32, chunk d / 32
+                double ut = __shfl_sync(kFull, u[0], d & 31);
+#pragma unroll
+                for (int cc = 1; cc < NR; ++cc) {
+                    const double tmp = __shfl_sync(kFull, u[cc], d & 31);
+                    ut = ((d >> 5) == cc) ? tmp : ut;
+                }
+                double *col = W + k + 1 + d;
+                if (cact) {
+                    for (int r0 = lr; r0 < nR; r0 += 4 * LR) {
+                        // offsets are clamped to the last listed row, so all four loads are
+                        // unconditional (a repeated element is simply not stored)
+                        unsigned off[4];
+                        double a[4], lm[4];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const int ri = min(r0 + b * LR, nR - 1);
+                            off[b] = (unsigned)rlist[ri] * (unsigned)S;
+                            lm[b] = scratch[ri];
+                        }
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) a[b] = col[off[b]];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const double nv = __dsub_rn(a[b], __dmul_rn(lm[b], ut));
+                            if (r0 + b * LR < nR) col[off[b]] = nv;
+                        }
+                    }
+                }
+            }
+            upd += 2ull * nzu * (unsigned)nR;
+        }
+        c.n_lu += upd;
+        DZ_STEP_TICK(PH_E_UPD)
+        return;
+    }
+#endif
     unsigned nrows = 0;
     bool nz[NR];
 #pragma unroll
@@ -894,20 +977,20 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
         if (c.wm && M <= 32 * WARP_NR_MAX) { // warp-per-LP fast path, NR = ceil(M/32)
             if (WARP_NR_MAX <= 4) {
                 if (M <= 32)
-                    warp_step_small<1>(c, W, k, is_ctl);
+                    warp_step_small<1>(c, W, k, is_ctl, y);
                 else if (M <= 64)
-                    warp_step_small<2>(c, W, k, is_ctl);
+                    warp_step_small<2>(c, W, k, is_ctl, y);
                 else if (M <= 96)
-                    warp_step_small<3>(c, W, k, is_ctl);
+                    warp_step_small<3>(c, W, k, is_ctl, y);
                 else
-                    warp_step_small<4>(c, W, k, is_ctl);
+                    warp_step_small<4>(c, W, k, is_ctl, y);
             } else {
                 if (M <= 160)
-                    warp_step_small<5>(c, W, k, is_ctl);
+                    warp_step_small<5>(c, W, k, is_ctl, y);
                 else if (M <= 192)
-                    warp_step_small<6>(c, W, k, is_ctl);
+                    warp_step_small<6>(c, W, k, is_ctl, y);
                 else
-                    warp_step_small<8>(c, W, k, is_ctl);
+                    warp_step_small<8>(c, W, k, is_ctl, y);
             }
             ++k;
             continue;
@@ -1232,10 +1315,14 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
         c.unitRow = ip, ip += M;
         c.pend = ip, ip += M;
         c.pre = ip, ip += M + 2;
+        c.clist = nullptr;
+#if DZ_STEP_TILED
+        if (WARP && NRMAX <= 4) c.clist = ip, ip += M + 2;
+#endif
         c.bsbuf = nullptr;
 #if DZ_BSUB_COMPACT
         if (WARP) {
-            ip += M & 1; // 7 M + 2 ints so far: keep the doubles 8-byte aligned
+            if ((reinterpret_cast<size_t>(ip) & 7) != 0) ++ip; // keep the doubles 8-byte aligned
             c.bsbuf = reinterpret_cast<double *>(ip);
             ip += 2 * M;
         }
@@ -1548,7 +1635,8 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
     if ((warps_hint < 0 || auto_warp) && without <= max_smem / 2 && M <= 1024) {
         // warp-per-LP: WPC independent warps per CTA, basis in the HBM workspace
         const size_t per_team =
-            (fixed_smem_bytes(true) + pvec_bytes_for(M) + (DZ_BSUB_COMPACT ? 8 * (size_t)M + 8 : 0) + 15) & ~(size_t)15;
+            (fixed_smem_bytes(true) + pvec_bytes_for(M) + (DZ_BSUB_COMPACT ? 8 * (size_t)M + 8 : 0) +
+             (DZ_STEP_TILED && M <= 128 ? 4 * ((size_t)M + 2) : 0) + 15) & ~(size_t)15;
         int wpc = (int)std::min<size_t>(4, max_smem / per_team);
         wpc = std::max(1, wpc);
         plan->warp_mode = true;
