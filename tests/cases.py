@@ -15,6 +15,8 @@ GOLDEN_WORKLOADS = {
     "mixed_20x40": lambda: generate.mixed_batch(48, 20, 40),
     "c2_32x64": lambda: generate.config2(48),
     "packing_24x48": lambda: generate.packing(16, 24, 48),
+    # lowered 120x280: ceil(m_int/32) == 4, the widest warp-per-LP fast path
+    "small_40x80": lambda: generate.small_batch(12, 40, 80),
     # the fragile family at a size where the reference's own arithmetic breaks
     # down on part of the seeds (false infeasible/unbounded, safe_divide panic)
     "mixed_60x120": lambda: generate.mixed_batch(12, 60, 120),
