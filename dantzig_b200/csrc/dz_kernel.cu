@@ -72,6 +72,8 @@
 //                    columns of the pivot row) instead of 32 consecutive columns: the pivot
 //                    row has a median of 5 nonzeros at config 2, so lanes-on-columns leaves most
 //                    lanes idle and needs one dependent round trip per pair of rows
+//   DZ_PRICE_BATCH   n > 0: pricing issues the loads of n column entries before the first add
+//                    needs one (branch-free theta lookups); measured neutral on config 2 in round 1
 //   DZ_NOINLINE      warp_step_small / warp_back_substitute_small as real functions, so that the
 //                    register allocator sees each hot loop on its own
 //   DZ_OPAQUE_LANE   the lane id of a warp team comes from %laneid through an opaque asm, so it
@@ -85,6 +87,9 @@
 #endif
 #ifndef DZ_STEP_TILED
 #define DZ_STEP_TILED 0
+#endif
+#ifndef DZ_PRICE_BATCH
+#define DZ_PRICE_BATCH 0
 #endif
 #ifndef DZ_NOINLINE
 #define DZ_NOINLINE 0
@@ -114,6 +119,15 @@ __device__ __forceinline__ double load_ref(const double *__restrict__ th, int re
     const double v = (ref >> 1) == 0 ? 1.0 : __ldg(th + (ref >> 1));
     return (ref & 1) ? -v : v;
 }
+
+#if DZ_PRICE_BATCH
+// Branch-free form for batched loads: theta[0] (= 1.0) stands in for the entries
+// that need no load, so a group of these has all its loads in flight at once.
+__device__ __forceinline__ double load_ref_nb(const double *__restrict__ th, int ref) {
+    const double v = __ldg(th + (ref < 0 ? 0 : (ref >> 1)));
+    return ref < 0 ? 0.0 : ((ref & 1) ? -v : v);
+}
+#endif
 
 // Total order used by every arg-max on the path: larger key first, then the
 // smaller index ("first index wins", simplex.rs:432-435, linalg.rs:100-105).
@@ -1434,6 +1448,31 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
                         const int e0 = T.col_ptr[col], e1 = T.col_ptr[col + 1];
                         double s = 0.0;
                         unsigned cntp = 0;
+#if DZ_PRICE_BATCH
+                        const bool use_lval = HOME == 2 && c.lval != nullptr;
+                        for (int e = e0; e < e1; e += DZ_PRICE_BATCH) {
+                            int ref[DZ_PRICE_BATCH], row[DZ_PRICE_BATCH];
+#pragma unroll
+                            for (int q = 0; q < DZ_PRICE_BATCH; ++q) {
+                                const bool ok = e + q < e1;
+                                ref[q] = ok ? (use_lval ? 0 : T.val_ref[e + q]) : -1;
+                                row[q] = ok ? T.row_idx[e + q] : 0;
+                            }
+                            double a[DZ_PRICE_BATCH], vr[DZ_PRICE_BATCH];
+#pragma unroll
+                            for (int q = 0; q < DZ_PRICE_BATCH; ++q) {
+                                a[q] = (use_lval && ref[q] >= 0) ? c.lval[e + q] : load_ref_nb(theta, ref[q]);
+                                vr[q] = c.vv[row[q]];
+                            }
+#pragma unroll
+                            for (int q = 0; q < DZ_PRICE_BATCH; ++q) {
+                                const double t = __dadd_rn(s, __dmul_rn(a[q], -vr[q]));
+                                const bool nz = (a[q] != 0.0);
+                                s = nz ? t : s;
+                                cntp += nz ? 2u : 0u;
+                            }
+                        }
+#else
 #pragma unroll 4
                         for (int e = e0; e < e1; ++e) {
                             const double a = c.lval ? c.lval[e] : load_ref(theta, T.val_ref[e]);
@@ -1442,6 +1481,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
                             s = nz ? t : s;
                             cntp += nz ? 2u : 0u;
                         }
+#endif
                         c.n_price += cntp;
                         c.dzv[k] = s;
                     }
