@@ -7,7 +7,11 @@
 
 #include "dz_internal.h"
 
+#ifdef DZ_EMU // test-only: g++ build of this file on the SIMT emulator of tests/emu (never the product)
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
 #include <cstdio>
 #include <cstring>

@@ -56,7 +56,11 @@
 
 #include "dz_internal.h"
 
+#ifdef DZ_EMU // test-only: g++ build of this file on the SIMT emulator of tests/emu (never the product)
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
 #include <algorithm>
 #include <cstdio>
@@ -1251,7 +1255,11 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
 template <int HOME, bool WARP, int NRMAX>
 __global__ void __launch_bounds__(WARP ? 128 : 1024, WARP ? (NRMAX <= 4 ? 8 : 4) : 1)
 dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team) {
+#ifdef DZ_EMU
+    unsigned char *smem_raw = emu::dyn_smem();
+#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
     Ctx c;
     c.M = T.M;
     c.Nn = T.Nn;
@@ -1636,8 +1644,13 @@ cudaError_t launch_one(const TemplateDev &T, const BatchDev &Bt, const LaunchPla
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          plan.smem_bytes);
     if (e != cudaSuccess) return e;
+#ifdef DZ_EMU
+    (void)st;
+    return emu::launch(kern, plan.grid, plan.block, (size_t)plan.smem_bytes, T, Bt, plan.smem_per_team);
+#else
     kern<<<plan.grid, plan.block, plan.smem_bytes, st>>>(T, Bt, plan.smem_per_team);
     return cudaGetLastError();
+#endif
 }
 
 } // namespace
@@ -1757,6 +1770,12 @@ int launch_batch(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &pla
     return DZ_OK;
 }
 
+#ifdef DZ_EMU
+int measure_fp64_peak(int, double *, double *, std::string *err) {
+    *err = "not available on the SIMT emulator";
+    return DZ_ERR_CUDA;
+}
+#else
 // ---------------------------------------------------------------------------
 // FP64 pipe micro-benchmark: the roofline denominator for the exact path.
 // ---------------------------------------------------------------------------
@@ -1828,5 +1847,7 @@ int measure_fp64_peak(int device, double *mul_sub_gflops, double *fma_gflops, st
     if (fma_gflops) *fma_gflops = res[1];
     return DZ_OK;
 }
+
+#endif // DZ_EMU
 
 } // namespace dz

@@ -1,0 +1,66 @@
+"""TEST INFRASTRUCTURE ONLY: runs in a subprocess whose DZ_LIB points at an
+emulator build (tests/emu/build_emu.py) and prints one JSON line of parity
+results against the golden fixtures / the oracle.
+
+    run_child.py golden <shapes: e.g. "-1:0,0:0,1:2"> <workload:count> ...
+    run_child.py kats
+"""
+import hashlib
+import json
+import os
+import struct
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from dantzig_b200 import Template, device_info, solve_batch, solve_model  # noqa: E402
+from tests import cases, kat  # noqa: E402
+
+bits = lambda x: struct.pack("<d", float(x)).hex()
+sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def golden(shapes, specs):
+    out = {}
+    for spec in specs:
+        wl, n = spec.split(":")
+        w = cases.GOLDEN_WORKLOADS[wl]()
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", wl + ".json")))
+        n = min(int(n), w.B)
+        for G, H in shapes:
+            res = solve_batch(Template(w.structure), w.theta[:n], worker_warps=G, basis_home=H)
+            bad = 0
+            for i in range(n):
+                e = g["lps"][i]
+                ok = (res.status[i], res.pivots[i], res.n_primal[i], int(res.trace_hash[i])) == (
+                    e["status"], e["pivots"], e["n_primal"], e["trace_hash"]) \
+                    and bits(res.objective[i]) == e["objective_bits"] and sha(res.values[i]) == e["values_sha"]
+                bad += (not ok)
+            out["%s@%d:%d" % (wl, G, H)] = [bad, n]
+    return out
+
+
+def kats():
+    from oracle import dzo_py
+
+    out = {}
+    for name, model, expect in kat.rust_kats():
+        s = solve_model(model)
+        o = dzo_py.lower(model).solve(dzo_py.LITERAL)
+        ok = (s.status, s.pivots, s.trace_hash) == (o.status, o.pivots, o.trace_hash)
+        if o.status == 0:
+            ok = ok and bits(s.objective) == bits(o.objective)
+        out[name] = [int(not ok), 1]
+    return out
+
+
+if __name__ == "__main__":
+    assert "emulator" in device_info(0)["name"].lower(), "run_child.py must run on an emulator build"
+    if sys.argv[1] == "golden":
+        shapes = [tuple(int(x) for x in s.split(":")) for s in sys.argv[2].split(",")]
+        print("EMU " + json.dumps(golden(shapes, sys.argv[3:])))
+    else:
+        print("EMU " + json.dumps(kats()))

@@ -1,0 +1,74 @@
+"""The CUDA kernel source, compiled by g++ on the SIMT emulator of tests/emu and
+checked against the golden fixtures on the CPU.
+
+This is test infrastructure: tests/emu/simt_emu.h runs every CUDA thread as a
+fiber and resolves warp collectives and block barriers, so the SAME kernel code
+(dantzig_b200/csrc/dz_kernel.cu, built with -DDZ_EMU) executes here without a
+GPU.  It checks the kernel's logic in every launch shape, and the off-by-default
+build variants (DZ_STEP_TILED, DZ_BSUB_COMPACT, ...) before they ever see a GPU.
+The product never builds or loads the emulated library; the parity tests proper
+are the `-m gpu` ones.
+"""
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+ALL_SHAPES = "0:0,-1:0,1:2,3:1,2:3"      # the five launch shapes of tests/test_gpu_parity.py
+
+
+def _build(name="", flags=()):
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(EMU, "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(name, list(flags))
+
+
+def _run(lib, *args):
+    env = dict(os.environ, DZ_LIB=lib)
+    r = subprocess.run([sys.executable, os.path.join(EMU, "run_child.py"), *args], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("EMU ")][-1]
+    return json.loads(line[4:])
+
+
+def _assert_clean(res):
+    bad = {k: v for k, v in res.items() if v[0] != 0}
+    assert not bad, bad
+    assert res and all(v[1] > 0 for v in res.values())
+
+
+def test_shipped_kernel_every_launch_shape():
+    lib = _build()
+    _assert_clean(_run(lib, "golden", ALL_SHAPES, "tiny_4x6:8", "small_8x16:4", "mixed_9x12:6",
+                       "mixed_20x40:2", "packing_24x48:1"))
+
+
+def test_shipped_kernel_warp_fast_paths():
+    """ceil(m_int/32) = 1..4 (64-register kernel) and 6 (128-register kernel), one warp per LP."""
+    lib = _build()
+    _assert_clean(_run(lib, "golden", "-1:0", "c2_32x64:2", "small_40x80:1", "c2_false_unbounded:1"))
+
+
+def test_reference_kats_through_the_c_abi():
+    lib = _build()
+    _assert_clean(_run(lib, "kats"))
+
+
+@pytest.mark.parametrize("name,flags", [
+    ("tiled", ["-DDZ_STEP_TILED=1"]),
+    ("bsub", ["-DDZ_BSUB_COMPACT=1", "-DDZ_BSUB_U32=1"]),
+    ("all", ["-DDZ_STEP_TILED=1", "-DDZ_BSUB_COMPACT=1", "-DDZ_BSUB_U32=1", "-DDZ_PRICE_BATCH=8",
+             "-DDZ_STEP_PROFILE=1"]),
+])
+def test_build_variants_keep_parity(name, flags):
+    """The off-by-default kernel variants (tools/README.md) on the shapes they touch."""
+    lib = _build(name, flags)
+    _assert_clean(_run(lib, "golden", "-1:0,0:0", "tiny_4x6:8", "mixed_9x12:6", "mixed_20x40:2",
+                       "packing_24x48:1", "c2_32x64:1", "small_40x80:1"))
