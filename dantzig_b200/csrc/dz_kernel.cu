@@ -76,6 +76,7 @@
 //                    columns of the pivot row) instead of 32 consecutive columns: the pivot
 //                    row has a median of 5 nonzeros at config 2, so lanes-on-columns leaves most
 //                    lanes idle and needs one dependent round trip per pair of rows
+//   DZ_STEP_U32      warp step: 32-bit unsigned offsets for the pivot-column and pivot-row loads
 //   DZ_PRICE_BATCH   n > 0: pricing issues the loads of n column entries before the first add
 //                    needs one (branch-free theta lookups); measured neutral on config 2 in round 1
 //   DZ_NOINLINE      warp_step_small / warp_back_substitute_small as real functions, so that the
@@ -91,6 +92,9 @@
 #endif
 #ifndef DZ_STEP_TILED
 #define DZ_STEP_TILED 0
+#endif
+#ifndef DZ_STEP_U32
+#define DZ_STEP_U32 0
 #endif
 #ifndef DZ_PRICE_BATCH
 #define DZ_PRICE_BATCH 0
@@ -640,7 +644,11 @@ DZ_HOT_FN void warp_step_small(Ctx &c, double *__restrict__ W, const int k, cons
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
         const int r = lane + 32 * i;
+#if DZ_STEP_U32
+        v[i] = (pos[i] >= k) ? W[(unsigned)r * (unsigned)S + (unsigned)k] : 0.0;
+#else
         v[i] = (pos[i] >= k) ? W[(size_t)r * S + k] : 0.0;
+#endif
     }
     unsigned bhi = 0u, blo = 0u;
     int bidx = 0x7fffffff;
@@ -666,7 +674,11 @@ DZ_HOT_FN void warp_step_small(Ctx &c, double *__restrict__ W, const int k, cons
     const int gi = __reduce_min_sync(kFull, (bhi == mh && blo == ml) ? bidx : 0x7fffffff);
     const int pr = gi & 0xffff, ppos = gi >> 16;
     DZ_STEP_TICK(PH_E_SEARCH) // column loads + arg-max
+#if DZ_STEP_U32
+    const double *__restrict__ prow = W + (unsigned)pr * (unsigned)S;
+#else
     const double *__restrict__ prow = W + (size_t)pr * S;
+#endif
     const double pv = prow[k];
     // pivot row, up to four chunks of 32 columns (column M is the right-hand side)
     double u[NR];
@@ -716,11 +728,13 @@ DZ_HOT_FN void warp_step_small(Ctx &c, double *__restrict__ W, const int k, cons
             if (need) {
                 const int t = nR + __popc(mk & lt);
                 rlist[t] = r;
-                scratch[t] = __ddiv_rn(v[i], pv);
+                scratch[t] = v[i]; // divided below, one pass over the compacted list
             }
             nR += __popc(mk);
             upd += need ? 1 : 0;
         }
+        __syncwarp();
+        for (int t = lane; t < nR; t += 32) scratch[t] = __ddiv_rn(scratch[t], pv); // multipliers l_ik
         __syncwarp();
         if (nR > 0 && nC > 0) {
             const int lgc = nC <= 4 ? 2 : (nC <= 8 ? 3 : (nC <= 16 ? 4 : 5));
