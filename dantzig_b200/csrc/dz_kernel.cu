@@ -76,6 +76,9 @@
 //                    columns of the pivot row) instead of 32 consecutive columns: the pivot
 //                    row has a median of 5 nonzeros at config 2, so lanes-on-columns leaves most
 //                    lanes idle and needs one dependent round trip per pair of rows
+//   DZ_KERNEL_PER_NR one warp-per-LP kernel per value of ceil(m_int/32) (1,2,3,4,5,6,8) holding only
+//                    its own fast paths, instead of one kernel with all of them plus the general
+//                    step: a third of the code per kernel (instruction cache)
 //   DZ_STEP_U32      warp step: 32-bit unsigned offsets for the pivot-column and pivot-row loads
 //   DZ_PRICE_BATCH   n > 0: pricing issues the loads of n column entries before the first add
 //                    needs one (branch-free theta lookups); measured neutral on config 2 in round 1
@@ -92,6 +95,9 @@
 #endif
 #ifndef DZ_STEP_TILED
 #define DZ_STEP_TILED 0
+#endif
+#ifndef DZ_KERNEL_PER_NR
+#define DZ_KERNEL_PER_NR 0
 #endif
 #ifndef DZ_STEP_U32
 #define DZ_STEP_U32 0
@@ -826,7 +832,7 @@ DZ_HOT_FN void warp_step_small(Ctx &c, double *__restrict__ W, const int k, cons
 
 // lu_solve (linalg.rs:8-10) of B (transposed == false, rhs = column `arg` of A)
 // or of B^T (transposed == true, rhs = e_arg).  Result in y[0..M).
-template <int WARP_NR_MAX>
+template <int WARP_NR_MAX, int NRX = 0> // NRX > 0: instantiated for exactly ceil(m_int/32) == NRX (DZ_KERNEL_PER_NR)
 __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
                                             const double *__restrict__ theta, bool transposed,
                                             int arg, double *y) {
@@ -1006,6 +1012,13 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             c.prof[PH_E_B1] += tq - tb1;
         }
         if (k >= M - 1) break;
+#if DZ_KERNEL_PER_NR
+        if constexpr (NRX > 0) {
+            warp_step_small<NRX>(c, W, k, is_ctl, y);
+            ++k;
+            continue;
+        }
+#endif
         if (c.wm && M <= 32 * WARP_NR_MAX) { // warp-per-LP fast path, NR = ceil(M/32)
             if (WARP_NR_MAX <= 4) {
                 if (M <= 32)
@@ -1237,6 +1250,11 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
     // ---- back substitution ------------------------------------------------------
     // (second trip only when a non-finite value appeared: redo without skipping)
     for (int literal = 0; literal < 2; ++literal) {
+#if DZ_KERNEL_PER_NR
+        if constexpr (NRX > 0)
+            warp_back_substitute_small<NRX>(c, y, literal != 0);
+        else
+#endif
         if (c.wm && WARP_NR_MAX <= 4 && M <= 32)
             warp_back_substitute_small<1>(c, y, literal != 0);
         else if (c.wm && WARP_NR_MAX <= 4 && M <= 64)
@@ -1266,7 +1284,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
 // is ever executed).  Otherwise one CTA per LP.
 // NRMAX: largest ceil(m_int/32) the warp fast paths are instantiated for: 4 (64
 // registers, 32 warps per SM) or 8 (128 registers, 16 warps per SM: config 5).
-template <int HOME, bool WARP, int NRMAX>
+template <int HOME, bool WARP, int NRMAX, int NRX = 0>
 __global__ void __launch_bounds__(WARP ? 128 : 1024, WARP ? (NRMAX <= 4 ? 8 : 4) : 1)
 dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team) {
 #ifdef DZ_EMU
@@ -1460,7 +1478,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
             bool failed = false;
             for (int pass = 0; pass < 2; ++pass) {
                 const bool transposed = (pass == 0) != primal_step;
-                basis_solve<NRMAX>(c, T, theta, transposed, transposed ? p : c.nb[q],
+                basis_solve<NRMAX, NRX>(c, T, theta, transposed, transposed ? p : c.nb[q],
                                    transposed ? c.vv : c.dxv);
                 if (transposed) {
                     // pricing: dz = -N^T v (simplex.rs:235, linalg.rs:199-207); each
@@ -1651,10 +1669,10 @@ size_t smem_bytes_for(int M, int Nn, int home) {
            (home <= 1 ? vec_bytes_for(M, Nn) : 0);
 }
 
-template <int HOME, bool WARP, int NRMAX>
+template <int HOME, bool WARP, int NRMAX, int NRX = 0>
 cudaError_t launch_one(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan,
                        cudaStream_t st) {
-    auto kern = dz_batch_kernel<HOME, WARP, NRMAX>;
+    auto kern = dz_batch_kernel<HOME, WARP, NRMAX, NRX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          plan.smem_bytes);
     if (e != cudaSuccess) return e;
@@ -1771,6 +1789,20 @@ int launch_batch(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &pla
                  std::string *err) {
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
+#if DZ_KERNEL_PER_NR
+    if (plan.warp_mode && T.M <= 256) {
+        switch ((T.M + 31) / 32) {
+        case 0:
+        case 1: e = launch_one<1, true, 4, 1>(T, Bt, plan, st); break;
+        case 2: e = launch_one<1, true, 4, 2>(T, Bt, plan, st); break;
+        case 3: e = launch_one<1, true, 4, 3>(T, Bt, plan, st); break;
+        case 4: e = launch_one<1, true, 4, 4>(T, Bt, plan, st); break;
+        case 5: e = launch_one<1, true, 8, 5>(T, Bt, plan, st); break;
+        case 6: e = launch_one<1, true, 8, 6>(T, Bt, plan, st); break;
+        default: e = launch_one<1, true, 8, 8>(T, Bt, plan, st); break;
+        }
+    } else
+#endif
     if (plan.warp_mode)
         e = T.M <= 128 ? launch_one<1, true, 4>(T, Bt, plan, st) : launch_one<1, true, 8>(T, Bt, plan, st);
     else

@@ -64,7 +64,8 @@ def test_reference_kats_through_the_c_abi():
 @pytest.mark.parametrize("name,flags", [
     ("tiled", ["-DDZ_STEP_TILED=1", "-DDZ_STEP_U32=1"]),
     ("bsub", ["-DDZ_BSUB_COMPACT=1", "-DDZ_BSUB_U32=1"]),
-    ("all", ["-DDZ_STEP_TILED=1", "-DDZ_BSUB_COMPACT=1", "-DDZ_BSUB_U32=1", "-DDZ_PRICE_BATCH=8",
+    ("pernr", ["-DDZ_KERNEL_PER_NR=1"]),
+    ("all", ["-DDZ_KERNEL_PER_NR=1", "-DDZ_STEP_TILED=1", "-DDZ_BSUB_COMPACT=1", "-DDZ_BSUB_U32=1", "-DDZ_PRICE_BATCH=8",
              "-DDZ_STEP_U32=1", "-DDZ_STEP_PROFILE=1"]),
 ])
 def test_build_variants_keep_parity(name, flags):
