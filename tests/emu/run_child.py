@@ -54,6 +54,18 @@ def kats():
         if o.status == 0:
             ok = ok and bits(s.objective) == bits(o.objective)
         out[name] = [int(not ok), 1]
+    for name, model, minimize, expect in kat.python_kats():          # tests/test_optimize.py: exact ==
+        s = solve_model(model)
+        ok = s.status == {"optimal": 0, "unbounded": 1, "infeasible": 2}[expect[0]]
+        if ok and expect[0] == "optimal":
+            ok = (-s.objective if minimize else s.objective) == expect[1] and \
+                all(s.values[v] == val for v, val in expect[2].items())
+        out["py:" + name] = [int(not ok), 1]
+    for name, model in cases.ragged_models():                        # empty / ragged / degenerate inputs
+        s = solve_model(model)
+        o = dzo_py.lower(model).solve(dzo_py.LITERAL)
+        ok = (s.status, s.pivots, s.trace_hash, bits(s.objective)) == (o.status, o.pivots, o.trace_hash, bits(o.objective))
+        out["ragged:" + name] = [int(not ok), 1]
     return out
 
 
