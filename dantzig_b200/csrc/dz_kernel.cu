@@ -84,6 +84,10 @@
 //                    needs one (branch-free theta lookups); measured neutral on config 2 in round 1
 //   DZ_NOINLINE      warp_step_small / warp_back_substitute_small as real functions, so that the
 //                    register allocator sees each hot loop on its own
+//   DZ_OPAQUE_BASE   the per-team shared-memory and workspace base pointers go through an opaque
+//                    asm, so the pointers derived from them are kept (or spilled) instead of being
+//                    rebuilt from %ctaid/%tid/parameters at every use (6 % of the issued instructions
+//                    of the profiled build were such rematerialisations)
 //   DZ_OPAQUE_LANE   the lane id of a warp team comes from %laneid through an opaque asm, so it
 //                    stays in a register instead of being rematerialised from %tid in loops
 //   DZ_STEP_PROFILE  with opt.profile, warp_step_small splits its cycles into the PH_E_* slots
@@ -112,6 +116,9 @@
 #define DZ_HOT_FN __device__ __noinline__
 #else
 #define DZ_HOT_FN __device__ __forceinline__
+#endif
+#ifndef DZ_OPAQUE_BASE
+#define DZ_OPAQUE_BASE 0
 #endif
 #ifndef DZ_OPAQUE_LANE
 #define DZ_OPAQUE_LANE 0
@@ -1319,6 +1326,10 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
     {
         double *sp = reinterpret_cast<double *>(smem_raw + (size_t)team_in_cta * smem_per_team);
         double *gp = Bt.gws + team * Bt.gws_stride;
+#if DZ_OPAQUE_BASE && !defined(DZ_EMU)
+        asm volatile("" : "+l"(sp));
+        asm volatile("" : "+l"(gp));
+#endif
         const size_t wsz = ((size_t)M * c.S + 1) & ~(size_t)1;
         if (HOME == 0) {
             c.W = sp;
