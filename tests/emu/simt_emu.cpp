@@ -49,7 +49,20 @@ void fiber_main() {
     std::abort(); // a finished fiber is never resumed
 }
 
+unsigned long long g_ops[16] = {0}; // warp-level collectives resolved, per kind (EMU_STATS=1 prints them at exit)
+
+struct StatsPrinter {
+    ~StatsPrinter() {
+        if (!std::getenv("EMU_STATS")) return;
+        static const char *names[] = {"none", "ballot", "shfl", "rmax_u", "rmin_u", "rmax_i", "rmin_i", "syncwarp", "syncthreads"};
+        std::fprintf(stderr, "simt_emu collectives:");
+        for (int i = 1; i <= 8; ++i) std::fprintf(stderr, " %s=%llu", names[i], g_ops[i]);
+        std::fprintf(stderr, "\n");
+    }
+} g_stats_printer;
+
 void resolve_warp(Thread **lane, int n_lanes, Op op) {
+    ++g_ops[op];
     uint64_t acc = 0;
     bool first = true;
     for (int l = 0; l < n_lanes; ++l) {
@@ -114,6 +127,7 @@ void run_block(Block &b) {
         for (const Thread &t : b.th)
             if (!t.done && t.wait != OP_SYNCTHREADS) all_bar = false;
         if (all_bar) {
+            ++g_ops[OP_SYNCTHREADS];
             for (Thread &t : b.th)
                 if (!t.done) t.wait = OP_NONE;
             continue;
