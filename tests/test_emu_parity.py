@@ -73,3 +73,21 @@ def test_build_variants_keep_parity(name, flags):
     lib = _build(name, flags)
     _assert_clean(_run(lib, "golden", "-1:0,0:0", "tiny_4x6:8", "mixed_9x12:6", "mixed_20x40:1"))
     _assert_clean(_run(lib, "golden", "-1:0", "packing_24x48:1", "c2_32x64:1", "small_40x80:1"))
+
+
+def test_gpu_suite_subset_on_the_emulator():
+    """The ctypes-facing part of tests/test_gpu_parity.py (KATs, ragged and random models,
+    integer-data batches in three launch shapes, the transportation family, pivot cap,
+    array-native entry) with the emulated library behind the binding.  The batch-parity
+    tests over whole fixtures are left to the GPU (minutes per shape here), and the
+    dantzig.rust extension links the real library, so it is not part of this run."""
+    lib = _build()
+    env = dict(os.environ, DZ_LIB=lib)
+    r = subprocess.run(
+        [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q",
+         "-x", "-p", "no:cacheprovider", "-k",
+         "not test_full_config2_properties and not test_batch_parity and not test_batch_order "
+         "and not rust_module and not through_the_module"],
+        env=env, capture_output=True, text=True, timeout=1200, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
