@@ -716,7 +716,7 @@ DZ_HOT_FN void warp_step_small(Ctx &c, double *__restrict__ W, const int k, cons
     DZ_STEP_TICK(PH_E_B2) // pivot row loads + interchange bookkeeping
     unsigned long long upd = 0;
 #if DZ_STEP_TILED
-    if constexpr (NR <= 4) {
+    {
         // Three per-warp lists in shared memory: the pivot row's nonzero columns (clist),
         // the rows to update and their multipliers (`pre` is idle outside the gather, this
         // solve's output vector `scratch` until the back-substitution).  The 32 lanes then
@@ -1382,7 +1382,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
         c.pre = ip, ip += M + 2;
         c.clist = nullptr;
 #if DZ_STEP_TILED
-        if (WARP && NRMAX <= 4) c.clist = ip, ip += M + 2;
+        if (WARP) c.clist = ip, ip += M + 2;
 #endif
         c.bsbuf = nullptr;
 #if DZ_BSUB_COMPACT
@@ -1732,7 +1732,7 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
         // warp-per-LP: WPC independent warps per CTA, basis in the HBM workspace
         const size_t per_team =
             (fixed_smem_bytes(true) + pvec_bytes_for(M) + (DZ_BSUB_COMPACT ? 8 * (size_t)M + 8 : 0) +
-             (DZ_STEP_TILED && M <= 128 ? 4 * ((size_t)M + 2) : 0) + 15) & ~(size_t)15;
+             (DZ_STEP_TILED ? 4 * ((size_t)M + 2) : 0) + 15) & ~(size_t)15;
         int wpc = (int)std::min<size_t>(4, max_smem / per_team);
         wpc = std::max(1, wpc);
         plan->warp_mode = true;
