@@ -72,7 +72,8 @@ def test_build_variants_keep_parity(name, flags):
     """The off-by-default kernel variants (tools/README.md) on the shapes they touch."""
     lib = _build(name, flags)
     _assert_clean(_run(lib, "golden", "-1:0,0:0", "tiny_4x6:8", "mixed_9x12:6", "mixed_20x40:1"))
-    _assert_clean(_run(lib, "golden", "-1:0", "packing_24x48:1", "c2_32x64:1", "small_40x80:1", "mixed_60x120:1"))
+    wide = ["mixed_60x120:1"] if name == "all" else []      # ceil(m_int/32) = 6: the 128-register kernel
+    _assert_clean(_run(lib, "golden", "-1:0", "packing_24x48:1", "c2_32x64:1", "small_40x80:1", *wide))
 
 
 def test_gpu_suite_subset_on_the_emulator():
