@@ -975,6 +975,7 @@ __device__ __forceinline__ void basis_solve(Ctx &c, const TemplateDev &T,
             // row already sits at position k (or whose column is empty) changes nothing,
             // so a run of such steps is checked 32 at a time against the current tables.
             const int cl = c.wm ? tid : tid - c.NWK;
+            __syncwarp(); // the control lane's interchange of the previous step is visible to every lane
             for (;;) {
                 const int kk = k + cl;
                 bool noop = false;

@@ -11,6 +11,7 @@
 
 #include "dzo.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -144,6 +145,126 @@ bool lu_solve(std::vector<double> &a, int n, std::vector<double> &b, bool skip) 
     std::vector<int> p((size_t)(n > 1 ? n - 1 : 0));
     factorize(a.data(), n, p.data(), skip);
     lu_apply(a.data(), p.data(), n, b.data(), skip);
+    return true;
+}
+
+// SPARSE variant of lu_solve (linalg.rs:8-10, 88-128, 282-299): the same floating
+// point operations in the same order as the SKIP variant, on rows stored as ordered
+// maps instead of a dense n x n array, so that a 70 000-row basis with two million
+// nonzeros (BASELINE configs[3] at full size) can be followed on a CPU at all.
+//   * row OBJECTS keep their identity; rowAt/posOf record the interchanges
+//     (linalg.rs:107-114 swaps columns k..n of two rows: the L part stays, which
+//     is the same as never moving it);
+//   * the right-hand side rides along with its row object, which performs the
+//     forward half of LU::solve (linalg.rs:286-291) inside the elimination with
+//     the same products b_k * l_ik in the same order;
+//   * absent entries are exact zeros; every skip is one the SKIP variant makes.
+// Returns false when a non-finite value shows up in a place where SKIP falls back
+// to dense rows (the caller then uses the dense SKIP variant, or gives up).
+struct SparseRows {
+    int n = 0;
+    std::vector<std::map<int, double>> rows; // row object -> (column -> value)
+    std::vector<double> rhs;                 // per row object
+    std::vector<std::vector<int>> col_rows;  // column -> row objects that ever held an entry there
+};
+
+bool lu_solve_sparse(SparseRows &S, std::vector<double> &out) {
+    const int n = S.n;
+    if (n <= 0) return false;
+    std::vector<int> rowAt((size_t)n), posOf((size_t)n);
+    for (int i = 0; i < n; ++i) rowAt[i] = posOf[i] = i;
+    std::vector<std::pair<int, int>> cand; // (position, row object)
+    double flops = 0.0, sflops = 0.0;
+    for (int k = 0; k + 1 < n; ++k) {
+        cand.clear();
+        for (int r : S.col_rows[k])
+            if (posOf[r] >= k && S.rows[r].count(k)) cand.emplace_back(posOf[r], r);
+        std::sort(cand.begin(), cand.end());
+        // linalg.rs:98-105: first row with the largest |a_ik|, strict '>'
+        const int inc = rowAt[k];
+        int mu = k;
+        {
+            auto it = S.rows[inc].find(k);
+            double magnitude = std::fabs(it == S.rows[inc].end() ? 0.0 : it->second);
+            for (auto &pc : cand) {
+                if (pc.second == inc) continue; // the incumbent at position k (it may have to be eliminated below)
+                const double c = std::fabs(S.rows[pc.second][k]);
+                if (c > magnitude) {
+                    mu = pc.first;
+                    magnitude = c;
+                }
+            }
+        }
+        if (mu != k) { // linalg.rs:107-114
+            const int rk = rowAt[k], rm = rowAt[mu];
+            rowAt[k] = rm;
+            rowAt[mu] = rk;
+            posOf[rm] = k;
+            posOf[rk] = mu;
+        }
+        const int pr = rowAt[k];
+        auto &prow = S.rows[pr];
+        auto pit = prow.find(k);
+        const double pivot = pit == prow.end() ? 0.0 : pit->second;
+        if (pivot == 0.0) continue; // linalg.rs:117
+        if (!std::isfinite(pivot) || !std::isfinite(S.rhs[pr])) return false;
+        for (auto it = prow.upper_bound(k); it != prow.end(); ++it)
+            if (!std::isfinite(it->second)) return false;
+        const double bk = S.rhs[pr];
+        for (auto &pc : cand) {
+            const int r = pc.second;
+            if (r == pr) continue;
+            auto &row = S.rows[r];
+            auto vit = row.find(k);
+            const double v = vit->second;
+            row.erase(vit); // the L part is never read again (the rhs rides along)
+            if (v == 0.0) continue;
+            const double l = v / pivot;
+            flops += 1.0;
+            if (!std::isfinite(l)) return false;
+            for (auto it = prow.upper_bound(k); it != prow.end(); ++it) {
+                if (it->second == 0.0) continue;
+                const double adjustment = l * it->second;
+                auto e = row.find(it->first);
+                if (e == row.end()) {
+                    row.emplace(it->first, 0.0 - adjustment);
+                    S.col_rows[it->first].push_back(r);
+                } else {
+                    e->second -= adjustment;
+                }
+                flops += 2.0;
+            }
+            if (bk != 0.0) { // linalg.rs:288-290
+                S.rhs[r] -= bk * l;
+                sflops += 2.0;
+            }
+        }
+    }
+    // linalg.rs:292-297
+    out.assign((size_t)n, 0.0);
+    bool poisoned = false; // a non-finite b_j turns every later 0 * b_j into NaN
+    for (int i = n - 1; i >= 0; --i) {
+        const int r = rowAt[i];
+        auto &row = S.rows[r];
+        double s = S.rhs[r];
+        double diag = 0.0;
+        if (poisoned) return false;
+        for (auto it = row.lower_bound(i); it != row.end(); ++it) {
+            if (it->first == i) {
+                diag = it->second;
+                continue;
+            }
+            const double u = it->second, bj = out[(size_t)it->first];
+            if ((u == 0.0 || bj == 0.0) && std::isfinite(bj) && std::isfinite(u)) continue;
+            s -= u * bj;
+            sflops += 2.0;
+        }
+        out[(size_t)i] = s / diag;
+        sflops += 1.0;
+        if (!std::isfinite(out[(size_t)i])) poisoned = i > 0;
+    }
+    g_lu_flops += flops;
+    g_solve_flops += sflops;
     return true;
 }
 
@@ -361,6 +482,7 @@ int find_second_pivot(double mu, const std::vector<double> &y, const std::vector
 struct Solver {
     const dzo_lowered *lp;
     bool skip;
+    bool sparse = false; // DZO_SPARSE: sparse rows, falling back to dense SKIP on non-finite values
     int M, Nn;
     std::vector<int32_t> b, n;
     std::vector<double> x, x_bar, z, z_bar;
@@ -393,8 +515,41 @@ struct Solver {
             }
         }
     }
+    // The same system as build_basis + rhs, as sparse row objects (DZO_SPARSE).
+    bool sparse_solve(bool transposed, int arg) {
+        SparseRows S;
+        S.n = M;
+        S.rows.resize((size_t)M);
+        S.rhs.assign((size_t)M, 0.0);
+        S.col_rows.resize((size_t)M);
+        for (int p = 0; p < M; ++p) {
+            const int col = b[p];
+            for (int64_t e = lp->A.col_ptr[col]; e < lp->A.col_ptr[col + 1]; ++e) {
+                const int r = lp->A.row_idx[e];
+                const int wr = transposed ? p : r, wc = transposed ? r : p;
+                S.rows[(size_t)wr][wc] = lp->A.val[e];
+                S.col_rows[(size_t)wc].push_back(wr);
+            }
+        }
+        if (transposed) {
+            S.rhs[(size_t)arg] = 1.0;
+        } else {
+            for (int64_t e = lp->A.col_ptr[arg]; e < lp->A.col_ptr[arg + 1]; ++e)
+                S.rhs[(size_t)lp->A.row_idx[e]] = lp->A.val[e];
+        }
+        return lu_solve_sparse(S, rhs);
+    }
     // solve_for_dx, simplex.rs:226-229
     bool solve_for_dx(int j) {
+        if (sparse && M > 0) {
+            const double f0 = g_lu_flops, f1 = g_solve_flops;
+            if (sparse_solve(false, j)) {
+                dx = rhs;
+                return true;
+            }
+            g_lu_flops = f0, g_solve_flops = f1;
+            if ((int64_t)M * M > (int64_t)1 << 28) return false; // no dense fallback at this size
+        }
         rhs.assign((size_t)M, 0.0);
         for (int64_t e = lp->A.col_ptr[j]; e < lp->A.col_ptr[j + 1]; ++e)
             rhs[lp->A.row_idx[e]] = lp->A.val[e];
@@ -405,10 +560,21 @@ struct Solver {
     }
     // solve_for_dz, simplex.rs:231-236 + neg_t_dot linalg.rs:199-207
     bool solve_for_dz(int pos_i) {
-        rhs.assign((size_t)M, 0.0);
-        rhs[pos_i] = 1.0;
-        build_basis(true);
-        if (!lu_solve(dense, M, rhs, skip)) return false;
+        bool done = false;
+        if (sparse && M > 0) {
+            const double f0 = g_lu_flops, f1 = g_solve_flops;
+            done = sparse_solve(true, pos_i);
+            if (!done) {
+                g_lu_flops = f0, g_solve_flops = f1;
+                if ((int64_t)M * M > (int64_t)1 << 28) return false;
+            }
+        }
+        if (!done) {
+            rhs.assign((size_t)M, 0.0);
+            rhs[pos_i] = 1.0;
+            build_basis(true);
+            if (!lu_solve(dense, M, rhs, skip)) return false;
+        }
         dz.resize((size_t)Nn);
         double flops = 0.0;
         for (int k = 0; k < Nn; ++k) {
@@ -504,7 +670,8 @@ int dzo_solve(const dzo_lowered *lp, int variant, int64_t max_pivots, dzo_result
               double *x_basic, int32_t *basis, double *values, int32_t *trace,
               int64_t trace_cap) {
     g_lu_flops = g_solve_flops = g_other_flops = 0.0;
-    Solver s(lp, variant == DZO_SKIP);
+    Solver s(lp, variant == DZO_SKIP || variant == DZO_SPARSE);
+    s.sparse = variant == DZO_SPARSE;
     int status = DZO_OPTIMAL;
     int64_t pivots = 0, n_primal = 0, n_dual = 0;
     uint64_t h = 0xcbf29ce484222325ULL;

@@ -47,7 +47,11 @@ enum {
  * reference does (two fresh dense LUs per pivot, no skipping) and is the
  * variant timed as the CPU baseline; SKIP elides operations whose operand is an
  * exact zero while every other operand is finite. */
-enum { DZO_LITERAL = 0, DZO_SKIP = 1 };
+enum { DZO_LITERAL = 0, DZO_SKIP = 1, DZO_SPARSE = 2 };
+/* DZO_SPARSE: the SKIP variant's operations in the SKIP variant's order on rows
+ * stored as ordered maps (no dense m x m array), so a lowered 70 000 x 170 000
+ * transportation LP can be followed.  Falls back to dense SKIP for a solve in
+ * which a non-finite value appears (when m*m fits), else reports DZO_PANIC. */
 
 /*
  * Model as handed to rust.solve(objective, constraints) (src/lib.rs:16-27):

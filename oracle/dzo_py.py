@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libdzo.so")
 
 OPTIMAL, UNBOUNDED, INFEASIBLE, PANIC, PIVOT_CAP = range(5)
-LITERAL, SKIP = 0, 1
+LITERAL, SKIP, SPARSE = 0, 1, 2
 STATUS_NAMES = ["optimal", "unbounded", "infeasible", "panic", "pivot_cap"]
 
 
