@@ -29,13 +29,17 @@ GOLDEN_WORKLOADS = {
     # (lowered 283x683).  Seeds 0 and 1: one optimal, one where the reference's own
     # arithmetic breaks down -- parity includes reproducing that outcome.
     "c1_100x200": lambda: generate.config1(seeds=(0, 1, 2)),
+    # BASELINE.json configs[4] unit: 64x128 LPs (lowered 192x448) of the config-5 batch.  Ids 184
+    # (safe_divide panic), 201 and 223 (false unbounded) are the non-optimal ones among the
+    # first 320 LPs of the batch; the others are optimal.
+    "c5_64x128": lambda: by_ids("c5", [0, 1, 2, 3, 184, 201, 223, 5]),
 }
 
 
 def by_ids(kind: str, ids):
     ids = np.asarray(ids)
-    if kind == "c2":
-        m, n, fam = 32, 64, 2
+    if kind in ("c2", "c5"):
+        m, n, fam = (32, 64, 2) if kind == "c2" else (64, 128, 5)
         senses = np.full(m, generate.LE, np.int32)
         free = np.zeros(n, bool)
     else:

@@ -30,7 +30,10 @@ def digest(a: np.ndarray) -> str:
 
 
 def main() -> None:
+    only = set(sys.argv[1:])          # optional: regenerate just the named workloads
     for name, make in GOLDEN_WORKLOADS.items():
+        if only and name not in only:
+            continue
         w = make()
         rows = []
         for i in range(w.B):

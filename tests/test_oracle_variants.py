@@ -31,6 +31,58 @@ def test_literal_equals_skip(oracle, wl):
         assert b.flops[0] <= a.flops[0]
 
 
+@pytest.mark.parametrize("wl", ["tiny_4x6", "small_8x16", "mixed_9x12", "mixed_20x40", "c2_32x64",
+                                "packing_24x48", "c2_false_unbounded"])
+def test_sparse_equals_skip(oracle, wl):
+    """The sparse-row variant (the only one that can follow config 4 at full size) does the
+    SKIP variant's operations in the SKIP variant's order."""
+    w = cases.GOLDEN_WORKLOADS[wl]()
+    for i in range(min(w.B, 6)):
+        lo = oracle.lower(model_from_theta(w.structure, w.theta[i]))
+        a, b = lo.solve(oracle.SKIP, trace_cap=4096), lo.solve(oracle.SPARSE, trace_cap=4096)
+        assert (a.status, a.pivots, a.trace_hash) == (b.status, b.pivots, b.trace_hash)
+        assert bits(a.objective) == bits(b.objective)
+        assert np.array_equal(a.x_basic, b.x_basic, equal_nan=True)
+        assert np.array_equal(a.values, b.values, equal_nan=True)
+
+
+def test_sparse_equals_skip_on_breakdown_and_sparse_families(oracle):
+    from dantzig_b200 import generate
+
+    from dantzig_b200.model import ModelBuilder
+
+    rng = np.random.default_rng(20261018)      # small integer models: ties, zero pivots, every outcome
+    seen = np.zeros(5, int)
+    for _ in range(300):
+        mb = ModelBuilder()
+        nv = int(rng.integers(1, 8))
+        vs = [mb.var(lb=[None, 0.0, -1.5][rng.integers(3)], ub=[None, 2.5, 4.0][rng.integers(3)])
+              for _ in range(nv)]
+        pick = lambda k: [(float(rng.integers(-3, 4)), vs[rng.integers(nv)]) for _ in range(k)]
+        mb.maximize(pick(int(rng.integers(0, 5))), float(rng.integers(-2, 3)))
+        for _ in range(int(rng.integers(0, 7))):
+            [mb.leq, mb.geq, mb.eq][rng.integers(3)](pick(int(rng.integers(0, 5))), float(rng.integers(-4, 5)))
+        model = mb.build()
+        if len(model.obj_var) + len(model.row_var) == 0:
+            continue
+        lo = oracle.lower(model)
+        a, b = lo.solve(oracle.SKIP, max_pivots=2000), lo.solve(oracle.SPARSE, max_pivots=2000)
+        seen[a.status] += 1
+        assert (a.status, a.pivots, a.trace_hash) == (b.status, b.pivots, b.trace_hash)
+        assert np.array_equal(a.x_basic, b.x_basic, equal_nan=True)
+    assert seen[:4].min() > 0
+    for seed, shape in ((0, (10, 10, 40, 1)), (1, (20, 20, 120, 3)), (2, (60, 60, 150, 5))):
+        lo = oracle.lower(generate.transportation_model(seed, *shape))
+        a, b = lo.solve(oracle.SKIP), lo.solve(oracle.SPARSE)
+        assert (a.status, a.pivots, a.trace_hash, bits(a.objective)) == (
+            b.status, b.pivots, b.trace_hash, bits(b.objective))
+        assert np.array_equal(a.x_basic, b.x_basic, equal_nan=True)
+    # config 4 at 1/8 scale, 40-pivot prefix: the dense SKIP variant needs ~20 s, the sparse one 0.1 s
+    lo = oracle.lower(generate.transportation_model(0, 1000, 1000, 2500, 10))
+    a, b = lo.solve(oracle.SKIP, max_pivots=12), lo.solve(oracle.SPARSE, max_pivots=12)
+    assert (a.status, a.pivots, a.trace_hash, bits(a.objective)) == (4, 12, b.trace_hash, bits(b.objective))
+
+
 def test_skip_variant_on_breakdown_cases(oracle):
     """Statuses other than optimal must agree too (non-finite values disable skipping)."""
     w = cases.GOLDEN_WORKLOADS["mixed_80x160_breakdown"]()
