@@ -24,8 +24,8 @@ NVCC_FLAGS = [
     "--fmad=false",
     "-Xcompiler", "-fPIC",
 ]
-LIB_SOURCES = ["dz_kernel.cu", "dz_capi.cu", "dz_lower.cpp"]
-LIB_HEADERS = ["dz_internal.h", os.path.join("..", "..", "include", "dantzig_b200.h")]
+LIB_SOURCES = ["dz_kernel.cu", "dz_core.cu", "dz_capi.cu", "dz_lower.cpp"]
+LIB_HEADERS = ["dz_internal.h", "dz_device.cuh", os.path.join("..", "..", "include", "dantzig_b200.h")]
 
 
 def _nvcc() -> str:

@@ -56,7 +56,7 @@ static int template_on_device(dz_template *t, int device, dz::TemplateDev *view)
     const dz::Template &h = t->host;
     const size_t nnz = h.row_idx.size();
     const size_t n_orig = h.orig_var.size();
-    const size_t total = (size_t)h.n_int + 1 + 2 * nnz + (size_t)h.n_int + 2 * (size_t)h.m +
+    const size_t total = (size_t)h.n_int + 1 + 2 * nnz + 3 * (size_t)h.n_int + 2 * (size_t)h.m +
                          (size_t)(h.n_int - h.m) + 2 * n_orig;
     std::vector<int32_t> blob;
     blob.reserve(total);
@@ -69,6 +69,7 @@ static int template_on_device(dz_template *t, int device, dz::TemplateDev *view)
     const size_t o_cp = push(cp32), o_ri = push(h.row_idx), o_vr = push(h.val_ref);
     const size_t o_c = push(h.c_ref), o_b = push(h.b_ref), o_b0 = push(h.basis0);
     const size_t o_n0 = push(h.nonbasis0), o_pi = push(h.pos_index), o_ni = push(h.neg_index);
+    const size_t o_sr = push(h.slack_row), o_tw = push(h.twin);
     DZ_CUDA(cudaSetDevice(device));
     dz_template::Dev d;
     d.device = device;
@@ -92,6 +93,8 @@ static int template_on_device(dz_template *t, int device, dz::TemplateDev *view)
     d.view.nonbasis0 = d.blob + o_n0;
     d.view.pos_index = d.blob + o_pi;
     d.view.neg_index = d.blob + o_ni;
+    d.view.slack_row = d.blob + o_sr;
+    d.view.twin = d.blob + o_tw;
     t->devs.push_back(d);
     *view = d.view;
     return DZ_OK;
@@ -113,7 +116,13 @@ struct dz_batch {
     size_t out_bytes = 0;
     dz::BatchDev bd{};
     double *d_gws = nullptr;
-    unsigned int *d_counter = nullptr;
+    unsigned int *d_counter = nullptr; // [4]: work queue, hand-over count, second work queue
+    // second launch behind the on-chip core kernel: the general kernel continues the LPs
+    // the core kernel handed over (dz_core.cu)
+    dz::LaunchPlan fb_plan;
+    double *d_fb_gws = nullptr;
+    int32_t *d_exo_list = nullptr;
+    unsigned char *d_exo_state = nullptr;
     // pinned staging for the download
     unsigned char *h_out = nullptr;
     size_t off_status = 0, off_pivots = 0, off_nprimal = 0, off_hash = 0, off_obj = 0,
@@ -285,7 +294,7 @@ int dz_batch_create(const dz_template *tc, int64_t B, const dz_options *opt, dz_
     const size_t theta_bytes = sizeof(double) * (size_t)B * (size_t)h.n_theta;
     if (cudaMalloc(&b->d_theta, std::max<size_t>(theta_bytes, 8)) != cudaSuccess ||
         cudaMalloc(&b->d_out, std::max<size_t>(b->out_bytes, 8)) != cudaSuccess ||
-        cudaMalloc(&b->d_counter, sizeof(unsigned int)) != cudaSuccess) {
+        cudaMalloc(&b->d_counter, 4 * sizeof(unsigned int)) != cudaSuccess) {
         g_err = "cudaMalloc failed for the batch buffers";
         cudaGetLastError();
         return fail(DZ_ERR_ALLOC);
@@ -319,6 +328,30 @@ int dz_batch_create(const dz_template *tc, int64_t B, const dz_options *opt, dz_
     bd.next_lp = b->d_counter;
     bd.gws = b->d_gws;
     bd.gws_stride = b->plan.gws_doubles_per_cta;
+    bd.exo_list = nullptr;
+    bd.exo_count = b->d_counter + 1;
+    bd.exo_state = nullptr;
+    bd.exo_stride = 0;
+    bd.resume = 0;
+    bd.next_lp2 = b->d_counter + 2;
+    if (b->plan.core_mode) {
+        const size_t Nn = (size_t)(h.n_int - h.m);
+        bd.exo_stride = (int64_t)align_up(8 * (2 * M + 2 * Nn + 3) + 4 * (M + Nn), 16);
+        // the fallback grid: CTA per LP with the working basis in an HBM workspace
+        rc = dz::plan_launch(b->opt.device, h.m, h.n_int - h.m, (int64_t)h.row_idx.size(),
+                             std::min<int64_t>(B, 296), 0, 0, 2, &b->fb_plan, &g_err);
+        if (rc != DZ_OK) return fail(rc);
+        const size_t fb_bytes = sizeof(double) * (size_t)b->fb_plan.gws_doubles_per_cta * (size_t)b->fb_plan.teams;
+        if (cudaMalloc(&b->d_exo_list, sizeof(int32_t) * (size_t)B) != cudaSuccess ||
+            cudaMalloc(&b->d_exo_state, (size_t)bd.exo_stride * (size_t)B) != cudaSuccess ||
+            (fb_bytes && cudaMalloc(&b->d_fb_gws, fb_bytes) != cudaSuccess)) {
+            g_err = "cudaMalloc failed for the hand-over buffers";
+            cudaGetLastError();
+            return fail(DZ_ERR_ALLOC);
+        }
+        bd.exo_list = b->d_exo_list;
+        bd.exo_state = b->d_exo_state;
+    }
     *out = b;
     return DZ_OK;
 }
@@ -331,6 +364,9 @@ void dz_batch_destroy(dz_batch *b) {
     cudaFree(b->d_out);
     cudaFree(b->d_counter);
     cudaFree(b->d_gws);
+    cudaFree(b->d_fb_gws);
+    cudaFree(b->d_exo_list);
+    cudaFree(b->d_exo_state);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -356,7 +392,7 @@ int dz_batch_solve(dz_batch *b) {
         return DZ_ERR_ARG;
     }
     DZ_CUDA(cudaSetDevice(b->opt.device));
-    DZ_CUDA(cudaMemsetAsync(b->d_counter, 0, sizeof(unsigned int), b->stream));
+    DZ_CUDA(cudaMemsetAsync(b->d_counter, 0, 4 * sizeof(unsigned int), b->stream));
     DZ_CUDA(cudaMemsetAsync(b->d_out + b->off_work, 0, sizeof(double) * (size_t)b->B * 4,
                             b->stream));
     DZ_CUDA(cudaEventRecord(b->ev0, b->stream));
@@ -367,6 +403,14 @@ int dz_batch_solve(dz_batch *b) {
                                     (size_t)b->plan.teams, b->stream));
     int rc = dz::launch_batch(b->tview, b->bd, b->plan, b->stream, &g_err);
     if (rc != DZ_OK) return rc;
+    if (b->plan.core_mode) { // the general kernel picks up what the core kernel handed over (usually nothing)
+        dz::BatchDev fb = b->bd;
+        fb.resume = 1;
+        fb.gws = b->d_fb_gws;
+        fb.gws_stride = b->fb_plan.gws_doubles_per_cta;
+        rc = dz::launch_batch(b->tview, fb, b->fb_plan, b->stream, &g_err);
+        if (rc != DZ_OK) return rc;
+    }
     DZ_CUDA(cudaEventRecord(b->ev1, b->stream));
     b->timed = true;
     return DZ_OK;
@@ -420,7 +464,7 @@ int dz_batch_last_timing(dz_batch *b, float *kernel_ms, int32_t *launches) {
     float ms = 0.f;
     DZ_CUDA(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
     if (kernel_ms) *kernel_ms = ms;
-    if (launches) *launches = 1;
+    if (launches) *launches = b->plan.core_mode ? 2 : 1;
     return DZ_OK;
 }
 

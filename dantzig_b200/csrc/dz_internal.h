@@ -17,6 +17,11 @@ struct Template {
     std::vector<int32_t> row_idx, val_ref;
     std::vector<int32_t> c_ref, b_ref, basis0, nonbasis0;
     std::vector<int32_t> orig_var, pos_index, neg_index;
+    // slack_row[col]: the row of a slack column (one entry, the constant +1.0), else -1.
+    // twin[col]: the column that is this column's exact negative (pos/neg of one original
+    // variable: same rows, same references with the opposite sign), else -1.
+    std::vector<int32_t> slack_row, twin;
+    uint64_t structure_hash = 0; // of the structural arrays the template was built from
     int32_t c0_ref = -1;
     // theta layout
     int32_t n_vars = 0, n_obj = 0, n_rows_user = 0;
@@ -43,6 +48,8 @@ struct TemplateDev {
     const int32_t *nonbasis0; // [Nn]
     const int32_t *pos_index; // [n_orig]
     const int32_t *neg_index; // [n_orig]
+    const int32_t *slack_row; // [Nint]
+    const int32_t *twin;      // [Nint]
 };
 
 // Device view of one batch: inputs and outputs, all in HBM.
@@ -66,6 +73,15 @@ struct BatchDev {
     unsigned int *next_lp; // work-queue counter
     double *gws;     // global workspace for the basis when it does not fit in smem
     int64_t gws_stride; // doubles per CTA
+    // Hand-over from the on-chip core kernel (dz_core.cu) to the general kernel: LP ids the
+    // core kernel gave up, each with the state of its pivot loop at that point.
+    int32_t *exo_list;        // [B]
+    unsigned int *exo_count;  // number of entries
+    unsigned char *exo_state; // [B][exo_stride]: x, xbar [M], z, zbar [Nn] f64; pivots, n_primal, hash i64;
+                              // basis [M], nonbasis [Nn] i32
+    int64_t exo_stride;
+    int32_t resume;           // general kernel: 1 = work items are exo_list[0..*exo_count), continued from exo_state
+    unsigned int *next_lp2;   // work-queue counter of that second launch
 };
 
 // Launch plan computed on the host (dz_kernel.cu).
@@ -76,6 +92,8 @@ struct LaunchPlan {
     int32_t smem_per_team = 0; // warp mode: shared-memory slab per warp
     int64_t teams = 0;         // CTAs (or warps) that own a workspace slab
     int64_t gws_doubles_per_cta = 0;
+    bool core_mode = false;    // on-chip coupled-core kernel (dz_core.cu)
+    int32_t core_cap_w = 0;    // its shared-memory capacity for the working core, in doubles
 };
 
 int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32_t warps_hint,
@@ -83,6 +101,11 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
 // Enqueue the batched solve on `stream` (cudaStream_t passed as void*).
 int launch_batch(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan, void *stream,
                  std::string *err);
+// dz_core.cu
+size_t core_fixed_smem_bytes(int M, int Nn, int NQ);
+int core_nq(int M); // rows-per-lane class of the core kernel (0: m_int too large for it)
+int launch_core(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan, void *stream,
+                std::string *err);
 int measure_fp64_peak(int device, double *mul_sub_gflops, double *fma_gflops, std::string *err);
 
 void set_error(const std::string &s);

@@ -54,13 +54,7 @@
 // records interchanges and runs ahead over virgin-unit steps; it and the serial
 // part of back-substitution live on the control warp (the warp itself if WARP).
 
-#include "dz_internal.h"
-
-#ifdef DZ_EMU // test-only: g++ build of this file on the SIMT emulator of tests/emu (never the product)
-#include "simt_emu.h"
-#else
-#include <cuda_runtime.h>
-#endif
+#include "dz_device.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -130,89 +124,6 @@
 namespace dz {
 
 namespace {
-
-constexpr int kMaxWarps = 32;
-constexpr unsigned kFull = 0xffffffffu;
-
-__device__ __forceinline__ double load_ref(const double *__restrict__ th, int ref) {
-    if (ref < 0) return 0.0;
-    // theta[0] is the constant 1.0 by contract (include/dantzig_b200.h): no load
-    const double v = (ref >> 1) == 0 ? 1.0 : __ldg(th + (ref >> 1));
-    return (ref & 1) ? -v : v;
-}
-
-#if DZ_PRICE_BATCH
-// Branch-free form for batched loads: theta[0] (= 1.0) stands in for the entries
-// that need no load, so a group of these has all its loads in flight at once.
-__device__ __forceinline__ double load_ref_nb(const double *__restrict__ th, int ref) {
-    const double v = __ldg(th + (ref < 0 ? 0 : (ref >> 1)));
-    return ref < 0 ? 0.0 : ((ref & 1) ? -v : v);
-}
-#endif
-
-// Total order used by every arg-max on the path: larger key first, then the
-// smaller index ("first index wins", simplex.rs:432-435, linalg.rs:100-105).
-__device__ __forceinline__ bool beats(double k2, int i2, double k1, int i1) {
-    return i2 >= 0 && (i1 < 0 || k2 > k1 || (k2 == k1 && i2 < i1));
-}
-
-template <int N> struct Cand {
-    double key[N];
-    int idx[N];
-};
-
-// Block-wide arg-max of N independent (key, idx) candidates with one barrier.
-// red_key/red_idx hold [2][N][kMaxWarps]; `parity` alternates between calls so
-// a slot is never rewritten before every thread has read it.
-// Only warps 0..nparts-1 hold candidates (warp-uniform), the others just wait
-// for the result.
-template <int N>
-__device__ __forceinline__ void block_argmax(Cand<N> &c, double *red_key, int *red_idx,
-                                             int &parity, int nparts, int tid, bool wm) {
-    const int warp = tid >> 5, lane = tid & 31;
-    const int nwarps = nparts;
-    if (warp < nparts) {
-#pragma unroll
-        for (int n = 0; n < N; ++n) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double k2 = __shfl_xor_sync(kFull, c.key[n], off);
-                const int i2 = __shfl_xor_sync(kFull, c.idx[n], off);
-                if (beats(k2, i2, c.key[n], c.idx[n])) {
-                    c.key[n] = k2;
-                    c.idx[n] = i2;
-                }
-            }
-        }
-    }
-    if (wm) return; // single warp: the butterfly left the result in every lane
-    double *rk = red_key + (size_t)parity * N * kMaxWarps;
-    int *ri = red_idx + (size_t)parity * N * kMaxWarps;
-    if (lane == 0 && warp < nparts) {
-#pragma unroll
-        for (int n = 0; n < N; ++n) {
-            rk[n * kMaxWarps + warp] = c.key[n];
-            ri[n * kMaxWarps + warp] = c.idx[n];
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-        double bk = rk[n * kMaxWarps];
-        int bi = ri[n * kMaxWarps];
-        for (int w = 1; w < nwarps; ++w) {
-            const double k2 = rk[n * kMaxWarps + w];
-            const int i2 = ri[n * kMaxWarps + w];
-            if (beats(k2, i2, bk, bi)) {
-                bk = k2;
-                bi = i2;
-            }
-        }
-        c.key[n] = bk;
-        c.idx[n] = bi;
-    }
-    parity ^= 1;
-}
 
 struct Ctx {
     // problem
@@ -1410,10 +1321,13 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
 
     for (;;) {
         csync(c);
-        if (tid == 0) c.ctl[CTL_LP] = (int)atomicAdd(Bt.next_lp, 1u);
+        if (tid == 0) c.ctl[CTL_LP] = (int)atomicAdd(Bt.resume ? Bt.next_lp2 : Bt.next_lp, 1u);
         csync(c);
-        const long long lp = (unsigned)c.ctl[CTL_LP];
-        if (lp >= Bt.B) break;
+        const long long item = (unsigned)c.ctl[CTL_LP];
+        // second launch behind the on-chip core kernel (dz_core.cu): the LPs it handed over,
+        // continued from the state they were in
+        if (item >= (Bt.resume ? (long long)*Bt.exo_count : Bt.B)) break;
+        const long long lp = Bt.resume ? (long long)Bt.exo_list[item] : item;
         const double *__restrict__ theta = Bt.theta + (size_t)lp * Bt.n_theta;
         c.n_lu = c.n_solve = c.n_price = 0;
         unsigned long long n_upd = 0;
@@ -1449,6 +1363,26 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
         int status = DZ_OPTIMAL;
         long long pivots = 0, n_primal = 0;
         unsigned long long hash = 0xcbf29ce484222325ULL;
+        if (Bt.resume) {
+            const unsigned char *st = Bt.exo_state + (size_t)item * Bt.exo_stride;
+            const double *sd = reinterpret_cast<const double *>(st);
+            const long long *sl = reinterpret_cast<const long long *>(sd + 2 * M + 2 * Nn);
+            const int *si = reinterpret_cast<const int *>(sl + 3);
+            for (int p = tid; p < M; p += c.nthreads) {
+                c.x[p] = sd[p];
+                c.xb[p] = sd[M + p];
+                c.bas[p] = si[p];
+            }
+            for (int k = tid; k < Nn; k += c.nthreads) {
+                c.z[k] = sd[2 * M + k];
+                c.zb[k] = sd[2 * M + Nn + k];
+                c.nb[k] = si[M + k];
+            }
+            pivots = sl[0];
+            n_primal = sl[1];
+            hash = (unsigned long long)sl[2];
+            csync(c);
+        }
         if (M == 0) status = DZ_BREAKDOWN; // 0x0 basis: the reference panics (linalg.rs:95)
 
         while (M > 0) {
@@ -1725,6 +1659,53 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
     // per-LP vectors do not fit (M in the thousands) everything moves to HBM.
     plan->warp_mode = false;
     plan->smem_per_team = 0;
+    plan->core_mode = false;
+    // On-chip coupled-core kernel (dz_core.cu): the default whenever m_int <= 256.  The hints
+    // that name one of the older launch shapes (worker_warps, basis_home 1..3) still select
+    // them; basis_home == 4 forces the core kernel.
+    {
+        const int nq = core_nq(M);
+        const size_t fixed = nq ? core_fixed_smem_bytes(M, Nn, nq) : 0;
+        const bool want = basis_home == 4 || (basis_home == 0 && warps_hint == 0);
+        if (want && nq && M >= 1 && fixed + 1024 <= max_smem) {
+            const size_t full = (size_t)M * (size_t)((M + 1) | 1) * 8;
+            int cps = 1;
+            if (cps_hint > 0) {
+                cps = cps_hint;
+            } else {
+                // as many CTAs per SM as still keep >= 3/4 of a full-size core on chip; never
+                // more CTAs than LPs
+                for (int t = 8; t >= 1; --t) {
+                    const size_t per_cta = per_sm / t - 1024;
+                    if (per_cta > fixed && per_cta - fixed >= full * 3 / 4) {
+                        cps = t;
+                        break;
+                    }
+                }
+                const int64_t need = (B + sms - 1) / sms;
+                if (need < cps) cps = (int)std::max<int64_t>(need, 1);
+            }
+            cps = std::max(1, std::min(cps, 16));
+            size_t per_cta = std::min<size_t>(per_sm / cps - 1024, max_smem);
+            if (per_cta < fixed + 64) per_cta = fixed + 64;
+            size_t cap_bytes = std::min(per_cta - fixed, (full + 15) & ~(size_t)15);
+            cap_bytes &= ~(size_t)15;
+            plan->core_mode = true;
+            plan->core_cap_w = (int32_t)(cap_bytes / 8);
+            plan->home = 4;
+            plan->worker_warps = nq <= 4 ? 3 : 7;
+            plan->w_in_smem = cap_bytes >= full;
+            plan->block = nq <= 4 ? 128 : 256;
+            plan->smem_bytes = (int32_t)(fixed + cap_bytes);
+            plan->ctas_per_sm = cps;
+            plan->gws_doubles_per_cta = (int64_t)((full + 15) / 8);
+            int64_t grid = (int64_t)sms * cps;
+            if (grid > B) grid = B;
+            plan->grid = (int32_t)std::max<int64_t>(grid, 1);
+            plan->teams = plan->grid;
+            return DZ_OK;
+        }
+    }
     // Auto: one warp per LP when the batch is large enough to fill the machine with
     // independent warps and the fast small-M step applies; measured on config 2:
     // 8.4 kLP/s (32 warps/SM) vs 5.3 kLP/s CTA-per-LP (profiles/).
@@ -1799,6 +1780,7 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
 
 int launch_batch(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan, void *stream,
                  std::string *err) {
+    if (plan.core_mode) return launch_core(T, Bt, plan, stream, err);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
 #if DZ_KERNEL_PER_NR

@@ -27,6 +27,25 @@ static inline int32_t mkref(int64_t index, bool negate) {
     return (int32_t)((index << 1) | (negate ? 1 : 0));
 }
 
+// FNV-1a over the arrays that decide the lowered structure (pack_theta refuses a model
+// whose numbers would land on another structure's columns).
+static uint64_t structure_hash(const dz_model *m) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    auto mix = [&](const void *p, size_t bytes) {
+        const unsigned char *b = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < bytes; ++i) h = (h ^ b[i]) * 0x100000001b3ULL;
+    };
+    const int64_t T = m->n_rows > 0 ? m->row_ptr[m->n_rows] : 0;
+    for (int32_t v = 0; v < m->n_vars; ++v) {
+        const unsigned char f[2] = {(unsigned char)(m->has_lb[v] != 0), (unsigned char)(m->has_ub[v] != 0)};
+        mix(f, 2);
+    }
+    if (m->n_obj) mix(m->obj_var, sizeof(int32_t) * (size_t)m->n_obj);
+    if (m->n_rows) mix(m->row_ptr, sizeof(int64_t) * ((size_t)m->n_rows + 1));
+    if (T) mix(m->row_var, sizeof(int32_t) * (size_t)T);
+    return h;
+}
+
 int build_template(const dz_model *m, Template *t, std::string *err) {
     if (!m || m->n_vars < 0 || m->n_obj < 0 || m->n_rows < 0) {
         *err = "dz_template_create: negative count in model";
@@ -203,6 +222,26 @@ int build_template(const dz_model *m, Template *t, std::string *err) {
         t->neg_index[k] = col_of_virtual[2 * k + 1];
     }
     t->c0_ref = mkref(1, false);
+    // (6) structure the kernels exploit without changing any value: slack columns (the
+    // only columns that are unit vectors by construction) and exact-negative twins.
+    t->slack_row.assign((size_t)Nint, -1);
+    for (int32_t j = 0; j < Nint; ++j)
+        if (t->col_ptr[j + 1] - t->col_ptr[j] == 1 && t->val_ref[t->col_ptr[j]] == mkref(0, false))
+            t->slack_row[j] = t->row_idx[t->col_ptr[j]];
+    t->twin.assign((size_t)Nint, -1);
+    for (int32_t k = 0; k < n_orig; ++k) {
+        const int32_t cp = t->pos_index[k], cn = t->neg_index[k];
+        const int64_t a0 = t->col_ptr[cp], a1 = t->col_ptr[cp + 1], b0 = t->col_ptr[cn];
+        bool same = (a1 - a0) == (t->col_ptr[cn + 1] - b0) && a1 > a0;
+        for (int64_t e = 0; same && e < a1 - a0; ++e)
+            same = t->row_idx[a0 + e] == t->row_idx[b0 + e] && (t->val_ref[a0 + e] ^ 1) == t->val_ref[b0 + e] &&
+                   t->val_ref[a0 + e] >= 0;
+        if (same && t->slack_row[cp] < 0 && t->slack_row[cn] < 0) {
+            t->twin[cp] = cn;
+            t->twin[cn] = cp;
+        }
+    }
+    t->structure_hash = structure_hash(m);
     return DZ_OK;
 }
 
@@ -211,6 +250,15 @@ int pack_theta(const Template *t, const dz_model *m, double *theta, std::string 
     if (m->n_vars != t->n_vars || m->n_obj != t->n_obj || m->n_rows != t->n_rows_user ||
         T != t->n_row_terms) {
         *err = "dz_template_pack_theta: model shape differs from the template's";
+        return DZ_ERR_ARG;
+    }
+    if ((m->n_vars > 0 && (!m->has_lb || !m->has_ub || !m->lb || !m->ub)) || (m->n_obj > 0 && (!m->obj_var || !m->obj_coef)) ||
+        (m->n_rows > 0 && (!m->row_ptr || !m->rhs)) || (T > 0 && (!m->row_var || !m->row_coef))) {
+        *err = "dz_template_pack_theta: missing array";
+        return DZ_ERR_ARG;
+    }
+    if (structure_hash(m) != t->structure_hash) {
+        *err = "dz_template_pack_theta: model structure (bound flags, variable indices) differs from the template's";
         return DZ_ERR_ARG;
     }
     theta[0] = 1.0;

@@ -134,7 +134,8 @@ typedef struct dz_options {
                              memory (lowest latency, few LPs per SM), 2 = HBM/L2
                              workspace (more LPs in flight per SM), 3 = basis AND
                              per-LP vectors in HBM (chosen automatically when they
-                             exceed shared memory: m in the thousands)                 */
+                             exceed shared memory: m in the thousands), 4 = the on-chip
+                             coupled-core kernel (the automatic choice for m_int <= 256) */
 } dz_options;
 void dz_options_default(dz_options *o);
 

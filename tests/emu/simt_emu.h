@@ -181,6 +181,12 @@ template <class T> inline T atomicAdd(T *p, T v) {
     *p = old + v;
     return old;
 }
+inline unsigned atomicOr(unsigned *p, unsigned v) {
+    const unsigned old = *p;
+    *p = old | v;
+    return old;
+}
+inline double __longlong_as_double(long long v) { return emu_unbits<double>((uint64_t)v); }
 inline int atomicMin(int *p, int v) {
     const int old = *p;
     *p = std::min(old, v);
