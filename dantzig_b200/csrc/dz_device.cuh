@@ -11,10 +11,6 @@
 #include <cuda_runtime.h>
 #endif
 
-#ifndef DZ_PRICE_BATCH
-#define DZ_PRICE_BATCH 0
-#endif
-
 namespace dz {
 
 namespace {
@@ -28,15 +24,6 @@ __device__ __forceinline__ double load_ref(const double *__restrict__ th, int re
     const double v = (ref >> 1) == 0 ? 1.0 : __ldg(th + (ref >> 1));
     return (ref & 1) ? -v : v;
 }
-
-#if DZ_PRICE_BATCH
-// Branch-free form for batched loads: theta[0] (= 1.0) stands in for the entries
-// that need no load, so a group of these has all its loads in flight at once.
-__device__ __forceinline__ double load_ref_nb(const double *__restrict__ th, int ref) {
-    const double v = __ldg(th + (ref < 0 ? 0 : (ref >> 1)));
-    return ref < 0 ? 0.0 : ((ref & 1) ? -v : v);
-}
-#endif
 
 // Total order used by every arg-max on the path: larger key first, then the
 // smaller index ("first index wins", simplex.rs:432-435, linalg.rs:100-105).

@@ -60,63 +60,18 @@
 #include <cstdio>
 #include <cstdlib>
 
-// Build-time variants kept for A/B runs (tools/gpu_ab.py); all default to the shipped code.
-//   DZ_BSUB_COMPACT  warp back-substitution: the nonzero products of a row are compacted into
-//                    shared memory in order and subtracted by a plain load+sub chain instead
-//                    of one ballot-driven shuffle per product
-//   DZ_BSUB_U32      warp back-substitution: 32-bit unsigned row offsets (the trick that paid in
-//                    the warp step)
-//   DZ_STEP_TILED    warp step update with the lanes tiled over (rows to update) x (nonzero
-//                    columns of the pivot row) instead of 32 consecutive columns: the pivot
-//                    row has a median of 5 nonzeros at config 2, so lanes-on-columns leaves most
-//                    lanes idle and needs one dependent round trip per pair of rows
+// Build-time switches.  The round-1 variants that lost their A/B on the GPU (tiled warp step,
+// compacted back-substitution, 32-bit offsets, batched pricing loads, no-inline, opaque bases:
+// profiles/r02_experiments.md) are gone; what is left:
 //   DZ_KERNEL_PER_NR one warp-per-LP kernel per value of ceil(m_int/32) (1,2,3,4,5,6,8) holding only
 //                    its own fast paths, instead of one kernel with all of them plus the general
-//                    step: a third of the code per kernel (instruction cache)
-//   DZ_STEP_U32      warp step: 32-bit unsigned offsets for the pivot-column and pivot-row loads
-//   DZ_PRICE_BATCH   n > 0: pricing issues the loads of n column entries before the first add
-//                    needs one (branch-free theta lookups); measured neutral on config 2 in round 1
-//   DZ_NOINLINE      warp_step_small / warp_back_substitute_small as real functions, so that the
-//                    register allocator sees each hot loop on its own
-//   DZ_OPAQUE_BASE   the per-team shared-memory and workspace base pointers go through an opaque
-//                    asm, so the pointers derived from them are kept (or spilled) instead of being
-//                    rebuilt from %ctaid/%tid/parameters at every use (6 % of the issued instructions
-//                    of the profiled build were such rematerialisations)
-//   DZ_OPAQUE_LANE   the lane id of a warp team comes from %laneid through an opaque asm, so it
-//                    stays in a register instead of being rematerialised from %tid in loops
+//                    step: a third of the code per kernel (instruction cache); +5 % on config 2,
+//                    on by default
 //   DZ_STEP_PROFILE  with opt.profile, warp_step_small splits its cycles into the PH_E_* slots
-#ifndef DZ_BSUB_COMPACT
-#define DZ_BSUB_COMPACT 0
-#endif
-#ifndef DZ_BSUB_U32
-#define DZ_BSUB_U32 0
-#endif
-#ifndef DZ_STEP_TILED
-#define DZ_STEP_TILED 0
-#endif
 #ifndef DZ_KERNEL_PER_NR
-#define DZ_KERNEL_PER_NR 0
+#define DZ_KERNEL_PER_NR 1
 #endif
-#ifndef DZ_STEP_U32
-#define DZ_STEP_U32 0
-#endif
-#ifndef DZ_PRICE_BATCH
-#define DZ_PRICE_BATCH 0
-#endif
-#ifndef DZ_NOINLINE
-#define DZ_NOINLINE 0
-#endif
-#if DZ_NOINLINE
-#define DZ_HOT_FN __device__ __noinline__
-#else
 #define DZ_HOT_FN __device__ __forceinline__
-#endif
-#ifndef DZ_OPAQUE_BASE
-#define DZ_OPAQUE_BASE 0
-#endif
-#ifndef DZ_OPAQUE_LANE
-#define DZ_OPAQUE_LANE 0
-#endif
 #ifndef DZ_STEP_PROFILE
 #define DZ_STEP_PROFILE 0
 #endif
@@ -142,8 +97,6 @@ struct Ctx {
     int *rlo, *rhi;
     double *pbuf; // [M + 32 * kMaxWarps] ordered nonzero products of one back-substitution row
     int *plist;   // [M] pending back-substitution rows, descending position
-    int *clist;    // [M + 2] DZ_STEP_TILED: dense indices of the pivot row's nonzero columns
-    double *bsbuf; // [M] DZ_BSUB_COMPACT: ordered nonzero products of one back-substitution row
     double *lval; // [nnz] this LP's lowered values, resolved once from theta (HOME == 2)
     int *cand_r;  // [M] rows with a nonzero in the current pivot column (found by the search)
     double *cand_v; // [M] ... and their values
@@ -461,11 +414,7 @@ DZ_HOT_FN void warp_back_substitute_small(Ctx &c, double *y, const bool literal)
     const double *__restrict__ W = c.W;
     double uu[NR], nu[NR], d = 0.0, rhs = 0.0, nd = 0.0, nrhs = 0.0;
     {
-#if DZ_BSUB_U32
-        const double *rowp = W + (unsigned)c.rowAt[M - 1] * (unsigned)S;
-#else
         const double *rowp = W + (size_t)c.rowAt[M - 1] * S;
-#endif
 #pragma unroll
         for (int cc = 0; cc < NR; ++cc) nu[cc] = 0.0;
         nd = rowp[M - 1];
@@ -478,11 +427,7 @@ DZ_HOT_FN void warp_back_substitute_small(Ctx &c, double *y, const bool literal)
         d = nd;
         rhs = nrhs;
         if (i > 0) { // prefetch row i-1 (its U entries do not depend on y)
-#if DZ_BSUB_U32
-            const double *rowp = W + (unsigned)c.rowAt[i - 1] * (unsigned)S;
-#else
             const double *rowp = W + (size_t)c.rowAt[i - 1] * S;
-#endif
 #pragma unroll
             for (int cc = 0; cc < NR; ++cc) {
                 const int j = i + lane + 32 * cc;
@@ -492,23 +437,6 @@ DZ_HOT_FN void warp_back_substitute_small(Ctx &c, double *y, const bool literal)
             nrhs = rowp[M];
         }
         double s = rhs;
-#if DZ_BSUB_COMPACT
-        int cnt = 0;
-#pragma unroll
-        for (int cc = 0; cc < NR; ++cc) {
-            const int j = i + 1 + lane + 32 * cc;
-            if (i + 1 + 32 * cc >= M) break;
-            const double yj = (j < M) ? y[j] : 0.0;
-            const bool take = literal ? (j < M) : (uu[cc] != 0.0 && yj != 0.0);
-            const unsigned mk = __ballot_sync(kFull, take);
-            if (take) c.bsbuf[cnt + __popc(mk & ((1u << lane) - 1u))] = __dmul_rn(uu[cc], yj);
-            cnt += __popc(mk);
-        }
-        __syncwarp();
-        ops += 2ull * (unsigned)cnt;
-#pragma unroll 4
-        for (int q = 0; q < cnt; ++q) s = __dsub_rn(s, c.bsbuf[q]); // ascending column order
-#else
 #pragma unroll
         for (int cc = 0; cc < NR; ++cc) {
             const int j = i + 1 + lane + 32 * cc;
@@ -523,7 +451,6 @@ DZ_HOT_FN void warp_back_substitute_small(Ctx &c, double *y, const bool literal)
                 s = __dsub_rn(s, __shfl_sync(kFull, t, b));
             }
         }
-#endif
         const double yi = (d == 1.0) ? s : __ddiv_rn(s, d);
         if (lane == 0) {
             y[i] = yi;
@@ -568,11 +495,7 @@ DZ_HOT_FN void warp_step_small(Ctx &c, double *__restrict__ W, const int k, cons
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
         const int r = lane + 32 * i;
-#if DZ_STEP_U32
-        v[i] = (pos[i] >= k) ? W[(unsigned)r * (unsigned)S + (unsigned)k] : 0.0;
-#else
         v[i] = (pos[i] >= k) ? W[(size_t)r * S + k] : 0.0;
-#endif
     }
     unsigned bhi = 0u, blo = 0u;
     int bidx = 0x7fffffff;
@@ -598,11 +521,7 @@ DZ_HOT_FN void warp_step_small(Ctx &c, double *__restrict__ W, const int k, cons
     const int gi = __reduce_min_sync(kFull, (bhi == mh && blo == ml) ? bidx : 0x7fffffff);
     const int pr = gi & 0xffff, ppos = gi >> 16;
     DZ_STEP_TICK(PH_E_SEARCH) // column loads + arg-max
-#if DZ_STEP_U32
-    const double *__restrict__ prow = W + (unsigned)pr * (unsigned)S;
-#else
     const double *__restrict__ prow = W + (size_t)pr * S;
-#endif
     const double pv = prow[k];
     // pivot row, up to four chunks of 32 columns (column M is the right-hand side)
     double u[NR];
@@ -626,83 +545,6 @@ DZ_HOT_FN void warp_step_small(Ctx &c, double *__restrict__ W, const int k, cons
     for (int cc = 0; cc < NR; ++cc) nzu += (u[cc] != 0.0) ? 1u : 0u;
     DZ_STEP_TICK(PH_E_B2) // pivot row loads + interchange bookkeeping
     unsigned long long upd = 0;
-#if DZ_STEP_TILED
-    {
-        // Three per-warp lists in shared memory: the pivot row's nonzero columns (clist),
-        // the rows to update and their multipliers (`pre` is idle outside the gather, this
-        // solve's output vector `scratch` until the back-substitution).  The 32 lanes then
-        // tile the nR x nC block of elements to update, four rows in flight per lane: the
-        // same elements get the same two operations as in the row-pair loop below.
-        const unsigned lt = (1u << lane) - 1u;
-        int *__restrict__ clist = c.clist;
-        int *__restrict__ rlist = c.pre;
-        int nC = 0, nR = 0;
-#pragma unroll
-        for (int cc = 0; cc < NR; ++cc) {
-            const bool nzc = u[cc] != 0.0;
-            const unsigned mk = __ballot_sync(kFull, nzc);
-            if (nzc) clist[nC + __popc(mk & lt)] = lane + 32 * cc;
-            nC += __popc(mk);
-        }
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-            const int r = lane + 32 * i;
-            const bool need = pos[i] >= k && r != pr && v[i] != 0.0;
-            const unsigned mk = __ballot_sync(kFull, need);
-            if (need) {
-                const int t = nR + __popc(mk & lt);
-                rlist[t] = r;
-                scratch[t] = v[i]; // divided below, one pass over the compacted list
-            }
-            nR += __popc(mk);
-            upd += need ? 1 : 0;
-        }
-        __syncwarp();
-        for (int t = lane; t < nR; t += 32) scratch[t] = __ddiv_rn(scratch[t], pv); // multipliers l_ik
-        __syncwarp();
-        if (nR > 0 && nC > 0) {
-            const int lgc = nC <= 4 ? 2 : (nC <= 8 ? 3 : (nC <= 16 ? 4 : 5));
-            const int LC = 1 << lgc, LR = 32 >> lgc;
-            const int lc = lane & (LC - 1), lr = lane >> lgc;
-            for (int cb = 0; cb < nC; cb += LC) { // warp-uniform: the shuffles below need every lane
-                const bool cact = cb + lc < nC;
-                const int d = cact ? clist[cb + lc] : 0; // column k + 1 + d; its value sits in lane d % 32, chunk d / 32
-                double ut = __shfl_sync(kFull, u[0], d & 31);
-#pragma unroll
-                for (int cc = 1; cc < NR; ++cc) {
-                    const double tmp = __shfl_sync(kFull, u[cc], d & 31);
-                    ut = ((d >> 5) == cc) ? tmp : ut;
-                }
-                double *col = W + k + 1 + d;
-                if (cact) {
-                    for (int r0 = lr; r0 < nR; r0 += 4 * LR) {
-                        // offsets are clamped to the last listed row, so all four loads are
-                        // unconditional (a repeated element is simply not stored)
-                        unsigned off[4];
-                        double a[4], lm[4];
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const int ri = min(r0 + b * LR, nR - 1);
-                            off[b] = (unsigned)rlist[ri] * (unsigned)S;
-                            lm[b] = scratch[ri];
-                        }
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) a[b] = col[off[b]];
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const double nv = __dsub_rn(a[b], __dmul_rn(lm[b], ut));
-                            if (r0 + b * LR < nR) col[off[b]] = nv;
-                        }
-                    }
-                }
-            }
-            upd += 2ull * nzu * (unsigned)nR;
-        }
-        c.n_lu += upd;
-        DZ_STEP_TICK(PH_E_UPD)
-        return;
-    }
-#endif
     unsigned nrows = 0;
     bool nz[NR];
 #pragma unroll
@@ -1216,17 +1058,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
     c.Nn = T.Nn;
     c.S = T.S; // (M + 1) | 1, read from the parameter bank wherever it is needed
     c.wm = WARP;
-#if DZ_OPAQUE_LANE
-    if (WARP) {
-        unsigned lid;
-        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lid));
-        c.tid = (int)lid;
-    } else {
-        c.tid = (int)threadIdx.x;
-    }
-#else
     c.tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
-#endif
     c.nthreads = WARP ? 32 : (int)blockDim.x;
     c.nwarps = WARP ? 1 : (int)(blockDim.x >> 5);
     c.G = WARP ? 1 : c.nwarps - 1;
@@ -1238,10 +1070,6 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
     {
         double *sp = reinterpret_cast<double *>(smem_raw + (size_t)team_in_cta * smem_per_team);
         double *gp = Bt.gws + team * Bt.gws_stride;
-#if DZ_OPAQUE_BASE && !defined(DZ_EMU)
-        asm volatile("" : "+l"(sp));
-        asm volatile("" : "+l"(gp));
-#endif
         const size_t wsz = ((size_t)M * c.S + 1) & ~(size_t)1;
         if (HOME == 0) {
             c.W = sp;
@@ -1292,18 +1120,6 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
         c.unitRow = ip, ip += M;
         c.pend = ip, ip += M;
         c.pre = ip, ip += M + 2;
-        c.clist = nullptr;
-#if DZ_STEP_TILED
-        if (WARP) c.clist = ip, ip += M + 2;
-#endif
-        c.bsbuf = nullptr;
-#if DZ_BSUB_COMPACT
-        if (WARP) {
-            if ((reinterpret_cast<size_t>(ip) & 7) != 0) ++ip; // keep the doubles 8-byte aligned
-            c.bsbuf = reinterpret_cast<double *>(ip);
-            ip += 2 * M;
-        }
-#endif
         if (HOME == 2) {
             c.rlo = ip, ip += M;
             c.rhi = ip, ip += M;
@@ -1434,31 +1250,6 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
                         const int e0 = T.col_ptr[col], e1 = T.col_ptr[col + 1];
                         double s = 0.0;
                         unsigned cntp = 0;
-#if DZ_PRICE_BATCH
-                        const bool use_lval = HOME == 2 && c.lval != nullptr;
-                        for (int e = e0; e < e1; e += DZ_PRICE_BATCH) {
-                            int ref[DZ_PRICE_BATCH], row[DZ_PRICE_BATCH];
-#pragma unroll
-                            for (int q = 0; q < DZ_PRICE_BATCH; ++q) {
-                                const bool ok = e + q < e1;
-                                ref[q] = ok ? (use_lval ? 0 : T.val_ref[e + q]) : -1;
-                                row[q] = ok ? T.row_idx[e + q] : 0;
-                            }
-                            double a[DZ_PRICE_BATCH], vr[DZ_PRICE_BATCH];
-#pragma unroll
-                            for (int q = 0; q < DZ_PRICE_BATCH; ++q) {
-                                a[q] = (use_lval && ref[q] >= 0) ? c.lval[e + q] : load_ref_nb(theta, ref[q]);
-                                vr[q] = c.vv[row[q]];
-                            }
-#pragma unroll
-                            for (int q = 0; q < DZ_PRICE_BATCH; ++q) {
-                                const double t = __dadd_rn(s, __dmul_rn(a[q], -vr[q]));
-                                const bool nz = (a[q] != 0.0);
-                                s = nz ? t : s;
-                                cntp += nz ? 2u : 0u;
-                            }
-                        }
-#else
 #pragma unroll 4
                         for (int e = e0; e < e1; ++e) {
                             const double a = c.lval ? c.lval[e] : load_ref(theta, T.val_ref[e]);
@@ -1467,7 +1258,6 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
                             s = nz ? t : s;
                             cntp += nz ? 2u : 0u;
                         }
-#endif
                         c.n_price += cntp;
                         c.dzv[k] = s;
                     }
@@ -1660,13 +1450,13 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
     plan->warp_mode = false;
     plan->smem_per_team = 0;
     plan->core_mode = false;
-    // On-chip coupled-core kernel (dz_core.cu): the default whenever m_int <= 256.  The hints
-    // that name one of the older launch shapes (worker_warps, basis_home 1..3) still select
-    // them; basis_home == 4 forces the core kernel.
+    // On-chip coupled-core kernel (dz_core.cu): basis_home == 4.  Bit-identical, but measured
+    // slower than the warp-per-LP shape on configs 2 and 5 (profiles/r02_experiments.md), so
+    // it is not an automatic choice.
     {
         const int nq = core_nq(M);
         const size_t fixed = nq ? core_fixed_smem_bytes(M, Nn, nq) : 0;
-        const bool want = basis_home == 4 || (basis_home == 0 && warps_hint == 0);
+        const bool want = basis_home == 4;
         if (want && nq && M >= 1 && fixed + 1024 <= max_smem) {
             const size_t full = (size_t)M * (size_t)((M + 1) | 1) * 8;
             int cps = 1;
@@ -1713,8 +1503,7 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
     if ((warps_hint < 0 || auto_warp) && without <= max_smem / 2 && M <= 1024) {
         // warp-per-LP: WPC independent warps per CTA, basis in the HBM workspace
         const size_t per_team =
-            (fixed_smem_bytes(true) + pvec_bytes_for(M) + (DZ_BSUB_COMPACT ? 8 * (size_t)M + 8 : 0) +
-             (DZ_STEP_TILED ? 4 * ((size_t)M + 2) : 0) + 15) & ~(size_t)15;
+            (fixed_smem_bytes(true) + pvec_bytes_for(M) + 15) & ~(size_t)15;
         int wpc = (int)std::min<size_t>(4, max_smem / per_team);
         wpc = std::max(1, wpc);
         plan->warp_mode = true;

@@ -30,8 +30,10 @@ def golden(shapes, specs):
         w = cases.GOLDEN_WORKLOADS[wl]()
         g = json.load(open(os.path.join(ROOT, "tests", "golden", wl + ".json")))
         n = min(int(n), w.B)
-        for G, H in shapes:
-            res = solve_batch(Template(w.structure), w.theta[:n], worker_warps=G, basis_home=H)
+        for shape in shapes:                      # worker_warps : basis_home [: ctas_per_sm]
+            G, H = shape[0], shape[1]
+            cps = shape[2] if len(shape) > 2 else 0
+            res = solve_batch(Template(w.structure), w.theta[:n], worker_warps=G, basis_home=H, ctas_per_sm=cps)
             bad = 0
             for i in range(n):
                 e = g["lps"][i]
@@ -39,7 +41,7 @@ def golden(shapes, specs):
                     e["status"], e["pivots"], e["n_primal"], e["trace_hash"]) \
                     and bits(res.objective[i]) == e["objective_bits"] and sha(res.values[i]) == e["values_sha"]
                 bad += (not ok)
-            out["%s@%d:%d" % (wl, G, H)] = [bad, n]
+            out["%s@%s" % (wl, ":".join(str(v) for v in shape))] = [bad, n]
     return out
 
 

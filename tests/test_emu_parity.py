@@ -4,8 +4,8 @@ checked against the golden fixtures on the CPU.
 This is test infrastructure: tests/emu/simt_emu.h runs every CUDA thread as a
 fiber and resolves warp collectives and block barriers, so the SAME kernel code
 (dantzig_b200/csrc/dz_kernel.cu, built with -DDZ_EMU) executes here without a
-GPU.  It checks the kernel's logic in every launch shape, and the off-by-default
-build variants (DZ_STEP_TILED, DZ_BSUB_COMPACT, ...) before they ever see a GPU.
+GPU.  It checks the kernel's logic in every launch shape, the on-chip core kernel
+(dz_core.cu) included, and the build switches before they ever see a GPU.
 The product never builds or loads the emulated library; the parity tests proper
 are the `-m gpu` ones.
 """
@@ -19,7 +19,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
-ALL_SHAPES = "0:0,-1:0,1:2,3:1,2:3"      # the five launch shapes of tests/test_gpu_parity.py
+ALL_SHAPES = "0:0,-1:0,1:2,3:1,2:3,0:4"  # the six launch shapes of tests/test_gpu_parity.py
 
 
 def _build(name="", flags=()):
@@ -61,19 +61,25 @@ def test_reference_kats_through_the_c_abi():
     _assert_clean(_run(lib, "kats"))
 
 
+def test_core_kernel_shapes_and_hand_over():
+    """The on-chip coupled-core kernel (basis_home=4): every rows-per-lane class it is
+    instantiated for that a CPU can afford, the false-unbounded LPs, and a shared-memory
+    budget so small that core rows overflow into the HBM workspace (ctas_per_sm=16)."""
+    lib = _build()
+    _assert_clean(_run(lib, "golden", "0:4", "c2_32x64:2", "small_40x80:1", "c2_false_unbounded:2",
+                       "packing_24x48:2"))
+    _assert_clean(_run(lib, "golden", "0:4:16", "mixed_20x40:2", "c2_32x64:1"))
+
+
 @pytest.mark.parametrize("name,flags", [
-    ("tiled", ["-DDZ_STEP_TILED=1", "-DDZ_STEP_U32=1"]),
-    ("bsub", ["-DDZ_BSUB_COMPACT=1", "-DDZ_BSUB_U32=1"]),
-    ("pernr", ["-DDZ_KERNEL_PER_NR=1"]),
-    ("all", ["-DDZ_KERNEL_PER_NR=1", "-DDZ_STEP_TILED=1", "-DDZ_BSUB_COMPACT=1", "-DDZ_BSUB_U32=1", "-DDZ_PRICE_BATCH=8",
-             "-DDZ_STEP_U32=1", "-DDZ_STEP_PROFILE=1"]),
+    ("allinone", ["-DDZ_KERNEL_PER_NR=0"]),
+    ("prof", ["-DDZ_STEP_PROFILE=1"]),
 ])
 def test_build_variants_keep_parity(name, flags):
-    """The off-by-default kernel variants (tools/README.md) on the shapes they touch."""
+    """The remaining build switches (tools/README.md) on the shapes they touch."""
     lib = _build(name, flags)
     _assert_clean(_run(lib, "golden", "-1:0,0:0", "tiny_4x6:8", "mixed_9x12:6", "mixed_20x40:1"))
-    wide = ["mixed_60x120:1"] if name == "all" else []      # ceil(m_int/32) = 6: the 128-register kernel
-    _assert_clean(_run(lib, "golden", "-1:0", "packing_24x48:1", "c2_32x64:1", "small_40x80:1", *wide))
+    _assert_clean(_run(lib, "golden", "-1:0", "packing_24x48:1", "c2_32x64:1", "small_40x80:1"))
 
 
 def test_gpu_suite_subset_on_the_emulator():

@@ -175,8 +175,8 @@ def test_array_native_front_door():
                       bounds=[(l, u) for l, u in zip(lb, ub)], method="highs")
         if ref.status == 0 and status[i] == 0:
             assert abs(obj[i] - ref.fun) <= 1e-9 * max(1.0, abs(ref.fun))
-        else:
-            assert {0: 0, 2: 2, 3: 1}.get(ref.status, -1) == status[i] or status[i] == 3
+        else:                # HiGHS: 2 infeasible, 3 unbounded.  This family is feasible and bounded by construction.
+            assert {0: 0, 2: 2, 3: 1}.get(ref.status, -1) == status[i]
 
 
 def test_empty_basis_is_breakdown():
@@ -202,14 +202,16 @@ def _check_batch(oracle, w, res, n_oracle, variant):
 
 
 @pytest.mark.parametrize("wl", sorted(cases.GOLDEN_WORKLOADS))
-@pytest.mark.parametrize("shape", [(0, 0), (-1, 0), (1, 2), (3, 1), (2, 3)],
-                         ids=["auto", "warp-per-lp", "cta-1warp-hbm", "cta-3warps-smem", "cta-all-hbm"])
+@pytest.mark.parametrize("shape", [(0, 0), (-1, 0), (1, 2), (3, 1), (2, 3), (0, 4)],
+                         ids=["auto", "warp-per-lp", "cta-1warp-hbm", "cta-3warps-smem", "cta-all-hbm", "core-on-chip"])
 def test_batch_parity(oracle, wl, shape):
     """Every launch shape (worker warps per LP, home of the working basis) must
     give the same bits: they only change which thread does which operation."""
     w = cases.GOLDEN_WORKLOADS[wl]()
     if w.m >= 100 and shape not in ((0, 0), (2, 3)):
         pytest.skip("config-1 size: auto and all-in-HBM shapes only (minutes on one warp)")
+    if w.m >= 64 and shape == (1, 2):
+        pytest.skip("config-5 size on one worker warp per CTA: minutes")
     t = Template(w.structure)
     res = solve_batch(t, w.theta, trace_cap=256, worker_warps=shape[0], basis_home=shape[1])
     g = json.load(open(os.path.join(GOLD, wl + ".json")))

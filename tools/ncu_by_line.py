@@ -1,6 +1,6 @@
 """Aggregate an ncu report's per-instruction samples by CUDA source line.
 
-usage: ncu_by_line.py report.ncu-rep lib.so 'kernel-substring' [top]
+usage: ncu_by_line.py report.ncu-rep lib.so 'kernel-substring' [top] [source.cu (default dz_kernel.cu)]
 Needs the .so the report was captured from (built with -lineinfo).
 Lines of inlined CUDA headers (shuffles, __ldg ...) are charged to the nearest
 preceding dz_kernel.cu line; a per-function summary follows the per-line table.
@@ -9,6 +9,8 @@ import csv, io, os, re, subprocess, sys, tempfile
 
 rep, so, pat = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+SRC = sys.argv[5] if len(sys.argv) > 5 else "dz_kernel.cu"
+STEM = SRC.rsplit(".", 1)[0]
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
@@ -20,7 +22,7 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
 line_of = {}
 for f in os.listdir(tmp):
-    if "dz_kernel.sm" not in f:
+    if STEM + ".sm" not in f and STEM not in f:
         continue
     txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
     cur_fn, cur_line, want = None, None, False
@@ -33,7 +35,7 @@ for f in os.listdir(tmp):
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
         if m:
-            if m.group(1).endswith("dz_kernel.cu"):
+            if m.group(1).endswith(SRC):
                 cur_line = int(m.group(2))
             continue
         m = re.match(r"\s*/\*([0-9a-f]{4,6})\*/", ln)
@@ -54,7 +56,7 @@ for r in data:
         v = int(r[ix[h]] or 0)
         if v:
             a["stalls"][h] = a["stalls"].get(h, 0) + v
-src = open("/root/repo/dantzig_b200/csrc/dz_kernel.cu").read().splitlines()
+src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dantzig_b200", "csrc", SRC)).read().splitlines()
 print(kname, "samples", tot_s, "warp-instr", tot_i)
 for line, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
     st = sorted(a["stalls"].items(), key=lambda kv: -kv[1])[:3]
@@ -65,7 +67,7 @@ for line, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
 # per-function summary: a line belongs to the last function header above it
 starts = [(i + 1, m.group(1)) for i, l in enumerate(src)
           for m in [re.match(r"(?:__device__ __forceinline__|__global__|static __device__)\s+[\w:<> ]*?\b(\w+)\(", l.strip())
-                    or re.match(r"(dz_batch_kernel)\(", l.strip())] if m]
+                    or re.match(r"(dz_batch_kernel|dz_core_kernel)\(", l.strip())] if m]
 fagg = {}
 for line, a in agg.items():
     name = "?"
