@@ -123,6 +123,9 @@ struct dz_batch {
     double *d_fb_gws = nullptr;
     int32_t *d_exo_list = nullptr;
     unsigned char *d_exo_state = nullptr;
+    // whole-GPU single-LP kernel (dz_grid.cu)
+    unsigned char *d_grid_ws = nullptr;
+    dz::GridDev grid{};
     // pinned staging for the download
     unsigned char *h_out = nullptr;
     size_t off_status = 0, off_pivots = 0, off_nprimal = 0, off_hash = 0, off_obj = 0,
@@ -334,12 +337,24 @@ int dz_batch_create(const dz_template *tc, int64_t B, const dz_options *opt, dz_
     bd.exo_stride = 0;
     bd.resume = 0;
     bd.next_lp2 = b->d_counter + 2;
-    if (b->plan.core_mode) {
+    if (b->plan.grid_mode) {
+        const long long wcap = (long long)M * (long long)((M + 1) | 1);
+        const size_t bytes = dz::grid_workspace(h.m, h.n_int - h.m, (long long)h.row_idx.size(), b->plan.grid, wcap,
+                                                nullptr, nullptr);
+        if (cudaMalloc(&b->d_grid_ws, bytes) != cudaSuccess) {
+            g_err = "cudaMalloc failed for the single-LP workspace";
+            cudaGetLastError();
+            return fail(DZ_ERR_ALLOC);
+        }
+        dz::grid_workspace(h.m, h.n_int - h.m, (long long)h.row_idx.size(), b->plan.grid, wcap, b->d_grid_ws, &b->grid);
+    }
+    if (b->plan.core_mode || b->plan.grid_mode) {
         const size_t Nn = (size_t)(h.n_int - h.m);
         bd.exo_stride = (int64_t)align_up(8 * (2 * M + 2 * Nn + 3) + 4 * (M + Nn), 16);
         // the fallback grid: CTA per LP with the working basis in an HBM workspace
         rc = dz::plan_launch(b->opt.device, h.m, h.n_int - h.m, (int64_t)h.row_idx.size(),
-                             std::min<int64_t>(B, 296), 0, 0, 2, &b->fb_plan, &g_err);
+                             std::min<int64_t>(B, 296), b->plan.grid_mode ? 4 : 0, 0, b->plan.grid_mode ? 3 : 2,
+                             &b->fb_plan, &g_err);
         if (rc != DZ_OK) return fail(rc);
         const size_t fb_bytes = sizeof(double) * (size_t)b->fb_plan.gws_doubles_per_cta * (size_t)b->fb_plan.teams;
         if (cudaMalloc(&b->d_exo_list, sizeof(int32_t) * (size_t)B) != cudaSuccess ||
@@ -351,6 +366,12 @@ int dz_batch_create(const dz_template *tc, int64_t B, const dz_options *opt, dz_
         }
         bd.exo_list = b->d_exo_list;
         bd.exo_state = b->d_exo_state;
+        // the general kernel's interval mode expects an all-zero working basis and leaves it so
+        if (fb_bytes && b->fb_plan.home == 2 && cudaMemset(b->d_fb_gws, 0, fb_bytes) != cudaSuccess) {
+            g_err = "cudaMemset failed for the fallback workspace";
+            cudaGetLastError();
+            return fail(DZ_ERR_CUDA);
+        }
     }
     *out = b;
     return DZ_OK;
@@ -365,6 +386,7 @@ void dz_batch_destroy(dz_batch *b) {
     cudaFree(b->d_counter);
     cudaFree(b->d_gws);
     cudaFree(b->d_fb_gws);
+    cudaFree(b->d_grid_ws);
     cudaFree(b->d_exo_list);
     cudaFree(b->d_exo_state);
     if (b->h_out) cudaFreeHost(b->h_out);
@@ -401,9 +423,15 @@ int dz_batch_solve(dz_batch *b) {
         DZ_CUDA(cudaMemsetAsync(b->d_gws, 0,
                                 sizeof(double) * (size_t)b->plan.gws_doubles_per_cta *
                                     (size_t)b->plan.teams, b->stream));
-    int rc = dz::launch_batch(b->tview, b->bd, b->plan, b->stream, &g_err);
+    int rc;
+    if (b->plan.grid_mode) {
+        DZ_CUDA(cudaMemsetAsync(b->grid.bar, 0, 4 * sizeof(unsigned), b->stream));
+        rc = dz::launch_grid(b->tview, b->bd, b->grid, b->plan, b->stream, &g_err);
+    } else {
+        rc = dz::launch_batch(b->tview, b->bd, b->plan, b->stream, &g_err);
+    }
     if (rc != DZ_OK) return rc;
-    if (b->plan.core_mode) { // the general kernel picks up what the core kernel handed over (usually nothing)
+    if (b->plan.core_mode || b->plan.grid_mode) { // the general kernel picks up what the core kernel handed over (usually nothing)
         dz::BatchDev fb = b->bd;
         fb.resume = 1;
         fb.gws = b->d_fb_gws;
@@ -464,7 +492,7 @@ int dz_batch_last_timing(dz_batch *b, float *kernel_ms, int32_t *launches) {
     float ms = 0.f;
     DZ_CUDA(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
     if (kernel_ms) *kernel_ms = ms;
-    if (launches) *launches = b->plan.core_mode ? 2 : 1;
+    if (launches) *launches = (b->plan.core_mode || b->plan.grid_mode) ? 2 : 1;
     return DZ_OK;
 }
 

@@ -84,6 +84,22 @@ struct BatchDev {
     unsigned int *next_lp2;   // work-queue counter of that second launch
 };
 
+// Workspace of the whole-GPU single-LP kernel (dz_grid.cu): pointers into one HBM allocation.
+struct GridDev {
+    double *x, *xb, *dxv, *vv, *ycore, *z, *zb, *dzv;
+    double *lval;  // [nnz] the LP's lowered values, resolved once from theta
+    double *pkey;  // [4 * CTAs] partial arg-max keys
+    double *jobd;  // job descriptor, doubles
+    double *W;     // working core, dense rows of (nr + 1) | 1 doubles
+    int *bas, *nb, *rowAt, *posOf, *rowcnt, *srow, *spos, *rmapR, *rlist, *pmap, *plist, *pivr, *pend;
+    int *list;     // rows with a nonzero in the current pivot column
+    int *where;    // column -> nonbasic slot k >= 0, or -1 - (basis position)
+    int *pidx, *bcnt, *job;
+    unsigned *bar;   // grid barrier: arrivals, generation
+    unsigned *rmask; // [nr][ceil(nr/32)] columns of each core row that may be nonzero
+    long long w_cap; // doubles available at W
+};
+
 // Launch plan computed on the host (dz_kernel.cu).
 struct LaunchPlan {
     int32_t grid = 0, block = 0, smem_bytes = 0, ctas_per_sm = 0, worker_warps = 1, home = 0;
@@ -92,6 +108,7 @@ struct LaunchPlan {
     int32_t smem_per_team = 0; // warp mode: shared-memory slab per warp
     int64_t teams = 0;         // CTAs (or warps) that own a workspace slab
     int64_t gws_doubles_per_cta = 0;
+    bool grid_mode = false;    // whole-GPU single-LP kernel (dz_grid.cu), cooperative launch
     bool core_mode = false;    // on-chip coupled-core kernel (dz_core.cu)
     int32_t core_cap_w = 0;    // its shared-memory capacity for the working core, in doubles
 };
@@ -105,6 +122,12 @@ int launch_batch(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &pla
 size_t core_fixed_smem_bytes(int M, int Nn, int NQ);
 int core_nq(int M); // rows-per-lane class of the core kernel (0: m_int too large for it)
 int launch_core(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan, void *stream,
+                std::string *err);
+// dz_grid.cu
+size_t grid_workspace(int M, int Nn, long long nnz, int nblocks, long long w_cap_doubles, unsigned char *base,
+                      GridDev *d);
+size_t grid_smem_bytes();
+int launch_grid(const TemplateDev &T, const BatchDev &Bt, const GridDev &D, const LaunchPlan &plan, void *stream,
                 std::string *err);
 int measure_fp64_peak(int device, double *mul_sub_gflops, double *fma_gflops, std::string *err);
 

@@ -1450,6 +1450,23 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
     plan->warp_mode = false;
     plan->smem_per_team = 0;
     plan->core_mode = false;
+    plan->grid_mode = false;
+    // Whole-GPU single-LP kernel (dz_grid.cu): one cooperative grid, one CTA per SM, for the
+    // few-and-large case (configs 3 and 4); basis_home == 5 forces it (tests use small grids
+    // through ctas_per_sm = number of CTAs, worker_warps = warps per CTA).
+    if (basis_home == 5 || (basis_home == 0 && warps_hint == 0 && M > 1024 && B <= 4)) {
+        plan->grid_mode = true;
+        plan->home = 5;
+        plan->block = basis_home == 5 && warps_hint > 0 ? 32 * std::min(warps_hint, 16) : 512;
+        plan->grid = basis_home == 5 && cps_hint > 0 ? cps_hint : sms;
+        plan->worker_warps = plan->block / 32;
+        plan->w_in_smem = false;
+        plan->smem_bytes = (int32_t)grid_smem_bytes();
+        plan->ctas_per_sm = 1;
+        plan->teams = 1;
+        plan->gws_doubles_per_cta = 0;
+        return DZ_OK;
+    }
     // On-chip coupled-core kernel (dz_core.cu): basis_home == 4.  Bit-identical, but measured
     // slower than the warp-per-LP shape on configs 2 and 5 (profiles/r02_experiments.md), so
     // it is not an automatic choice.

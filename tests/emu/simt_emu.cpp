@@ -94,9 +94,9 @@ void resolve_warp(Thread **lane, int n_lanes, Op op) {
 
 } // namespace
 
-void run_block(Block &b) {
-    g_blk = &b;
-    const size_t n = b.th.size();
+namespace {
+
+void init_block(Block &b) {
     for (Thread &t : b.th) {
         void *st = nullptr;
         if (posix_memalign(&st, 64, kStackBytes) != 0) std::abort();
@@ -111,55 +111,108 @@ void run_block(Block &b) {
         t.done = false;
         t.wait = OP_NONE;
     }
-    size_t live = n;
-    while (live) {
-        bool progressed = false;
-        for (Thread &t : b.th) {
-            if (t.done || t.wait != OP_NONE) continue;
-            g_cur = &t;
-            emu_switch(&g_sched_sp, t.sp);
-            progressed = true;
-            if (t.done) --live;
+}
+
+size_t live_threads(const Block &b) {
+    size_t n = 0;
+    for (const Thread &t : b.th) n += t.done ? 0 : 1;
+    return n;
+}
+
+// One scheduling round of a block: run every runnable thread up to its next collective, then
+// resolve the block barrier or the warp collectives that are complete.  Returns whether anything
+// moved.  Threads waiting at a grid barrier are left to run_grid.
+bool step_block(Block &b) {
+    g_blk = &b;
+    const size_t n = b.th.size();
+    bool progressed = false;
+    for (Thread &t : b.th) {
+        if (t.done || t.wait != OP_NONE) continue;
+        g_cur = &t;
+        emu_switch(&g_sched_sp, t.sp);
+        progressed = true;
+    }
+    if (!live_threads(b)) return progressed;
+    // block barrier: every live thread has arrived
+    bool all_bar = true;
+    for (const Thread &t : b.th)
+        if (!t.done && t.wait != OP_SYNCTHREADS) all_bar = false;
+    if (all_bar) {
+        ++g_ops[OP_SYNCTHREADS];
+        for (Thread &t : b.th)
+            if (!t.done) t.wait = OP_NONE;
+        return true;
+    }
+    // warp collectives: every live lane of the warp waits at the same kind of operation
+    for (size_t w0 = 0; w0 < n; w0 += 32) {
+        Thread *lane[32] = {nullptr};
+        const int nl = (int)std::min<size_t>(32, n - w0);
+        Op op = OP_NONE;
+        bool uniform = true, any = false;
+        for (int l = 0; l < nl; ++l) {
+            Thread &t = b.th[w0 + (size_t)l];
+            if (t.done) continue;
+            lane[l] = &t;
+            if (!any) op = t.wait, any = true;
+            else if (t.wait != op) uniform = false;
         }
-        if (!live) break;
-        // block barrier: every live thread has arrived
-        bool all_bar = true;
-        for (const Thread &t : b.th)
-            if (!t.done && t.wait != OP_SYNCTHREADS) all_bar = false;
-        if (all_bar) {
-            ++g_ops[OP_SYNCTHREADS];
-            for (Thread &t : b.th)
-                if (!t.done) t.wait = OP_NONE;
-            continue;
+        if (!any || op == OP_NONE || op == OP_SYNCTHREADS || op == OP_GRIDSYNC) continue;
+        if (!uniform) {
+            std::fprintf(stderr, "simt_emu: block %u warp %zu diverged across different collectives\n",
+                         b.bid.x, w0 / 32);
+            std::abort();
         }
-        // warp collectives: every live lane of the warp waits at the same kind of operation
-        for (size_t w0 = 0; w0 < n; w0 += 32) {
-            Thread *lane[32] = {nullptr};
-            const int nl = (int)std::min<size_t>(32, n - w0);
-            Op op = OP_NONE;
-            bool uniform = true, any = false;
-            for (int l = 0; l < nl; ++l) {
-                Thread &t = b.th[w0 + (size_t)l];
-                if (t.done) continue;
-                lane[l] = &t;
-                if (!any) op = t.wait, any = true;
-                else if (t.wait != op) uniform = false;
-            }
-            if (!any || op == OP_NONE || op == OP_SYNCTHREADS) continue;
-            if (!uniform) {
-                std::fprintf(stderr, "simt_emu: block %u warp %zu diverged across different collectives\n",
-                             b.bid.x, w0 / 32);
-                std::abort();
-            }
-            resolve_warp(lane, nl, op);
-            progressed = true;
-        }
-        if (!progressed) {
+        resolve_warp(lane, nl, op);
+        progressed = true;
+    }
+    return progressed;
+}
+
+void fini_block(Block &b) {
+    for (Thread &t : b.th) std::free(t.stack);
+}
+
+} // namespace
+
+void run_block(Block &b) {
+    init_block(b);
+    while (live_threads(b)) {
+        if (!step_block(b)) {
             std::fprintf(stderr, "simt_emu: deadlock in block %u (a barrier some threads never reach)\n", b.bid.x);
             std::abort();
         }
     }
-    for (Thread &t : b.th) std::free(t.stack);
+    fini_block(b);
+    g_blk = nullptr;
+    g_cur = nullptr;
+}
+
+void run_grid(std::vector<Block> &blocks) {
+    for (Block &b : blocks) init_block(b);
+    for (;;) {
+        size_t live = 0;
+        bool progressed = false;
+        for (Block &b : blocks) {
+            if (!live_threads(b)) continue;
+            progressed = step_block(b) || progressed;
+            live += live_threads(b);
+        }
+        if (!live) break;
+        if (progressed) continue;
+        // nothing can move inside any block: the grid barrier, if every live thread is at it
+        bool all_grid = true;
+        for (const Block &b : blocks)
+            for (const Thread &t : b.th)
+                if (!t.done && t.wait != OP_GRIDSYNC) all_grid = false;
+        if (!all_grid) {
+            std::fprintf(stderr, "simt_emu: deadlock in a cooperative grid (a barrier some threads never reach)\n");
+            std::abort();
+        }
+        for (Block &b : blocks)
+            for (Thread &t : b.th)
+                if (!t.done) t.wait = OP_NONE;
+    }
+    for (Block &b : blocks) fini_block(b);
     g_blk = nullptr;
     g_cur = nullptr;
 }

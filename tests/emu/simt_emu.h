@@ -45,7 +45,7 @@
 
 namespace emu {
 
-enum Op { OP_NONE = 0, OP_BALLOT, OP_SHFL, OP_RMAX_U, OP_RMIN_U, OP_RMAX_I, OP_RMIN_I, OP_SYNCWARP, OP_SYNCTHREADS };
+enum Op { OP_NONE = 0, OP_BALLOT, OP_SHFL, OP_RMAX_U, OP_RMIN_U, OP_RMAX_I, OP_RMIN_I, OP_SYNCWARP, OP_SYNCTHREADS, OP_GRIDSYNC };
 
 struct Dim3 {
     unsigned x = 1, y = 1, z = 1;
@@ -85,6 +85,9 @@ inline uint64_t collective(Op op, uint64_t in, int aux) {
 }
 
 void run_block(Block &b);
+// Cooperative launch: every block of the grid is resident at once (fibers of all blocks are
+// scheduled round robin) and grid_sync() is a barrier over all of them.
+void run_grid(std::vector<Block> &blocks);
 
 template <class Kern, class... Args>
 int launch(Kern kern, int grid, int block, size_t smem_bytes, Args... args) {
@@ -106,7 +109,31 @@ int launch(Kern kern, int grid, int block, size_t smem_bytes, Args... args) {
     return 0;
 }
 
+template <class Kern, class... Args>
+int launch_coop(Kern kern, int grid, int block, size_t smem_bytes, Args... args) {
+    std::vector<Block> blocks((size_t)grid);
+    std::vector<void *> mem;
+    for (int bx = 0; bx < grid; ++bx) {
+        Block &b = blocks[(size_t)bx];
+        b.bid.x = (unsigned)bx;
+        b.bdim.x = (unsigned)block;
+        b.gdim.x = (unsigned)grid;
+        void *sm = nullptr;
+        if (posix_memalign(&sm, 128, smem_bytes + 128) != 0) return 2;
+        std::memset(sm, 0xA5, smem_bytes + 128);
+        mem.push_back(sm);
+        b.smem = static_cast<unsigned char *>(sm);
+        b.th.resize((size_t)block);
+        for (int t = 0; t < block; ++t) b.th[(size_t)t].tid.x = (unsigned)t;
+        b.body = [=]() { kern(args...); };
+    }
+    run_grid(blocks);
+    for (void *m : mem) std::free(m);
+    return 0;
+}
+
 inline unsigned char *dyn_smem() { return g_blk->smem; }
+inline void grid_sync() { collective(OP_GRIDSYNC, 0, 0); }
 
 } // namespace emu
 
@@ -187,6 +214,12 @@ inline unsigned atomicOr(unsigned *p, unsigned v) {
     return old;
 }
 inline double __longlong_as_double(long long v) { return emu_unbits<double>((uint64_t)v); }
+inline unsigned atomicExch(unsigned *p, unsigned v) {
+    const unsigned old = *p;
+    *p = v;
+    return old;
+}
+inline void __threadfence() {}
 inline int atomicMin(int *p, int v) {
     const int old = *p;
     *p = std::min(old, v);
@@ -255,6 +288,10 @@ inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) 
 }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t) {
     return cudaMemcpy(d, s, n, k);
+}
+inline cudaError_t cudaMemset(void *d, int v, size_t n) {
+    if (n) std::memset(d, v, n);
+    return cudaSuccess;
 }
 inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) {
     if (n) std::memset(d, v, n);

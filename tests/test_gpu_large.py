@@ -63,12 +63,12 @@ def test_config3_full_size_prefix(oracle):
     _same(r, o, cap)
 
 
-@pytest.mark.parametrize("scale,cap", [(1000, 40), (10000, 30)], ids=["eighth-scale", "full-size"])
-def test_config4_prefix(oracle, scale, cap):
+@pytest.mark.parametrize("scale,arcs,cap", [(1000, 2500, 40), (10000, 50000, 60)], ids=["eighth-scale", "full-size"])
+def test_config4_prefix(oracle, scale, arcs, cap):
     """BASELINE configs[3]: transportation-style sparse LP, `scale` supply + `scale` demand
-    rows, 2.5*scale arcs with 10+10 nonzeros each.  Full size is lowered 70000x170000 with
-    2.17 M nonzeros; the oracle follows it with sparse rows."""
-    model = generate.transportation_model(0, scale, scale, int(2.5 * scale), 10)
+    rows, `arcs` columns with 10+10 nonzeros each.  Full size (m=20k x n=50k) is lowered
+    70000x170000 with 2.17 M nonzeros; the oracle follows it with sparse rows."""
+    model = generate.transportation_model(0, scale, scale, arcs, 10)
     t = Template(model)
     r = _gpu_prefix(t, t.pack_theta(model), cap)
     o = oracle.lower(model).solve(oracle.SPARSE, max_pivots=cap, trace_cap=cap)
