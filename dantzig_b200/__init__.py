@@ -14,12 +14,12 @@ There is no CPU fallback: importing works everywhere, solving needs a GPU.
 from .model import EQ, GE, LE, ModelArrays, ModelBuilder, dense_structure, dense_theta  # noqa: F401
 from .solver import (  # noqa: F401
     BREAKDOWN, INFEASIBLE, OPTIMAL, PIVOT_CAP, UNBOUNDED, Batch, BatchResult, Solution, Template,
-    device_count, device_info, measure_fp64_peak, solve_batch, solve_dense_batch, solve_model,
+    device_count, device_info, measure_fp64_peak, solve_batch, solve_batch_multi, solve_dense_batch, solve_model,
 )
 
 __all__ = [
     "ModelArrays", "ModelBuilder", "dense_structure", "dense_theta", "LE", "GE", "EQ",
-    "Template", "Batch", "BatchResult", "Solution", "solve_batch", "solve_dense_batch", "solve_model",
+    "Template", "Batch", "BatchResult", "Solution", "solve_batch", "solve_batch_multi", "solve_dense_batch", "solve_model",
     "device_count", "device_info", "measure_fp64_peak",
     "OPTIMAL", "UNBOUNDED", "INFEASIBLE", "BREAKDOWN", "PIVOT_CAP",
 ]

@@ -9,7 +9,12 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("DZ_LIB", os.path.join(_PKG, "libdantzig_b200.so"))
+LIB_PATH = os.path.join(_PKG, "libdantzig_b200.so")
+# Test-only override: the CPU suite points the binding at the SIMT-emulator build of the same
+# sources (tests/emu).  Honoured only together with DZ_LIB_TEST_ONLY=1, which nothing but the
+# test harness sets, so a stray DZ_LIB cannot turn the product into a CPU path.
+if os.environ.get("DZ_LIB") and os.environ.get("DZ_LIB_TEST_ONLY") == "1":
+    LIB_PATH = os.environ["DZ_LIB"]
 
 OK, ERR_ARG, ERR_CUDA, ERR_LIMIT, ERR_ALLOC = 0, -1, -2, -3, -4
 OPTIMAL, UNBOUNDED, INFEASIBLE, BREAKDOWN, PIVOT_CAP = range(5)
@@ -19,7 +24,7 @@ STATUS_NAMES = ["optimal", "unbounded", "infeasible", "breakdown", "pivot_cap"]
 SYMBOLS = [
     "dz_template_create", "dz_template_destroy", "dz_template_get_info",
     "dz_template_get_arrays", "dz_template_pack_theta", "dz_options_default",
-    "dz_solve_batch", "dz_batch_create", "dz_batch_destroy", "dz_batch_upload",
+    "dz_solve_batch", "dz_solve_batch_multi", "dz_batch_create", "dz_batch_destroy", "dz_batch_upload",
     "dz_batch_solve", "dz_batch_download", "dz_batch_sync", "dz_batch_last_timing",
     "dz_batch_launch_info", "dz_batch_io_bytes", "dz_solve_model", "dz_last_error",
     "dz_device_count", "dz_device_info", "dz_version", "dz_measure_fp64_peak",
@@ -100,6 +105,7 @@ def lib() -> C.CDLL:
     L.dz_options_default.argtypes = [C.POINTER(Options)]
     L.dz_options_default.restype = None
     L.dz_solve_batch.argtypes = [vp, i64, vp, C.POINTER(Options), C.POINTER(BatchResult)]
+    L.dz_solve_batch_multi.argtypes = [vp, i64, vp, i32, C.POINTER(Options), C.POINTER(BatchResult)]
     L.dz_batch_create.argtypes = [vp, i64, C.POINTER(Options), C.POINTER(vp)]
     L.dz_batch_destroy.argtypes = [vp]
     L.dz_batch_destroy.restype = None

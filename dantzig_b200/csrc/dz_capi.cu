@@ -17,6 +17,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <thread>
 
 namespace dz {
 static thread_local std::string g_err;
@@ -290,7 +291,7 @@ int dz_batch_create(const dz_template *tc, int64_t B, const dz_options *opt, dz_
     b->off_values = place(sizeof(double) * (size_t)B * n_orig);
     b->off_x = place(sizeof(double) * (size_t)B * M);
     b->off_basis = place(sizeof(int32_t) * (size_t)B * M);
-    b->off_work = place(sizeof(double) * (size_t)B * 4);
+    b->off_work = place(sizeof(double) * (size_t)B * 8);
     b->off_trace = place(sizeof(int32_t) * (size_t)B * tc3);
     b->off_prof = place(b->opt.profile ? sizeof(int64_t) * (size_t)B * 16 : 0);
     b->out_bytes = off;
@@ -415,7 +416,7 @@ int dz_batch_solve(dz_batch *b) {
     }
     DZ_CUDA(cudaSetDevice(b->opt.device));
     DZ_CUDA(cudaMemsetAsync(b->d_counter, 0, 4 * sizeof(unsigned int), b->stream));
-    DZ_CUDA(cudaMemsetAsync(b->d_out + b->off_work, 0, sizeof(double) * (size_t)b->B * 4,
+    DZ_CUDA(cudaMemsetAsync(b->d_out + b->off_work, 0, sizeof(double) * (size_t)b->B * 8,
                             b->stream));
     DZ_CUDA(cudaEventRecord(b->ev0, b->stream));
     if (b->plan.home == 2) // interval mode expects an all-zero working basis (see dz_kernel.cu);
@@ -475,7 +476,7 @@ int dz_batch_download(dz_batch *b, dz_batch_result *out) {
     DZ_CUDA(get(out->values, b->off_values, sizeof(double) * B * n_orig));
     DZ_CUDA(get(out->x_basic, b->off_x, sizeof(double) * B * M));
     DZ_CUDA(get(out->basis, b->off_basis, sizeof(int32_t) * B * M));
-    DZ_CUDA(get(out->work, b->off_work, sizeof(double) * B * 4));
+    DZ_CUDA(get(out->work, b->off_work, sizeof(double) * B * 8));
     if (tc3) DZ_CUDA(get(out->trace, b->off_trace, sizeof(int32_t) * B * tc3));
     if (b->opt.profile) DZ_CUDA(get(out->prof, b->off_prof, sizeof(int64_t) * B * 16));
     DZ_CUDA(cudaStreamSynchronize(b->stream));
@@ -536,21 +537,145 @@ int dz_solve_batch(const dz_template *t, int64_t B, const double *theta, const d
     return rc;
 }
 
+int dz_solve_batch_multi(const dz_template *t, int64_t B, const double *theta, int32_t n_gpus,
+                         const dz_options *opt, dz_batch_result *out) {
+    if (!t || !theta || !out || B <= 0) {
+        g_err = "dz_solve_batch_multi: bad argument";
+        return DZ_ERR_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_err = "no CUDA device available (the solver has no CPU path)";
+        return DZ_ERR_CUDA;
+    }
+    if (n_gpus <= 0) n_gpus = ndev;
+    if (n_gpus > ndev) {
+        g_err = "dz_solve_batch_multi: more devices requested than are visible";
+        return DZ_ERR_ARG;
+    }
+    const dz::Template &h = t->host;
+    const size_t M = (size_t)h.m, n_orig = h.orig_var.size();
+    dz_options base;
+    if (opt)
+        base = *opt;
+    else
+        dz_options_default(&base);
+    base.stream = nullptr; // one library-owned stream per device
+    const size_t tc3 = (size_t)std::max(0, base.trace_cap) * 3;
+    std::vector<int> rcs((size_t)n_gpus, DZ_OK);
+    std::vector<std::string> errs((size_t)n_gpus);
+    auto shard = [&](int d) {
+        const int64_t lo = B * d / n_gpus, hi = B * (d + 1) / n_gpus;
+        if (hi <= lo) return;
+        dz_options o = base;
+        o.device = d;
+        dz_batch_result r = *out;
+        auto adv = [&](auto *&ptr, size_t per_lp) {
+            if (ptr) ptr += (size_t)lo * per_lp;
+        };
+        adv(r.status, 1), adv(r.pivots, 1), adv(r.n_primal, 1), adv(r.trace_hash, 1), adv(r.objective, 1);
+        adv(r.values, n_orig), adv(r.x_basic, M), adv(r.basis, M), adv(r.trace, tc3), adv(r.work, 8), adv(r.prof, 16);
+        rcs[(size_t)d] = dz_solve_batch(t, hi - lo, theta + (size_t)lo * (size_t)h.n_theta, &o, &r);
+        if (rcs[(size_t)d] != DZ_OK) errs[(size_t)d] = g_err; // this thread's message
+    };
+    std::vector<std::thread> threads;
+    for (int d = 1; d < n_gpus; ++d) threads.emplace_back(shard, d);
+    shard(0);
+    for (auto &th : threads) th.join();
+    for (int d = 0; d < n_gpus; ++d)
+        if (rcs[(size_t)d] != DZ_OK) {
+            g_err = "device " + std::to_string(d) + ": " + errs[(size_t)d];
+            return rcs[(size_t)d];
+        }
+    return DZ_OK;
+}
+
+// dz_solve_model keeps the template and a device-resident batch of one per model STRUCTURE
+// (and option set) it has seen, so that solving many small models of the same shape -- the
+// frontend's dz.Minimize(...).solve() in a loop -- pays lowering, cudaMalloc and stream
+// creation once, not per call.  A handful of entries, least recently used out first.
+namespace {
+struct ModelCacheEntry {
+    uint64_t key = 0;
+    int32_t n_vars = 0, n_obj = 0, n_rows = 0;
+    int64_t n_terms = 0;
+    dz_options opt{};
+    dz_template *t = nullptr;
+    dz_batch *b = nullptr;
+    uint64_t stamp = 0;
+};
+struct ModelCache {
+    std::mutex mu;
+    std::vector<ModelCacheEntry> entries;
+    uint64_t clock = 0;
+    // entries still cached at process exit are left to the driver (the CUDA runtime may be
+    // gone by the time static destructors run)
+};
+ModelCache g_model_cache;
+constexpr size_t kModelCacheEntries = 8;
+
+bool same_options(const dz_options &a, const dz_options &b) {
+    return a.device == b.device && a.max_pivots == b.max_pivots && a.trace_cap == b.trace_cap &&
+           a.worker_warps == b.worker_warps && a.ctas_per_sm == b.ctas_per_sm && a.stream == b.stream &&
+           a.profile == b.profile && a.basis_home == b.basis_home;
+}
+} // namespace
+
 int dz_solve_model(const dz_model *model, const dz_options *opt, dz_solution *sol,
                    double *values) {
     if (!model || !sol) {
         g_err = "dz_solve_model: NULL argument";
         return DZ_ERR_ARG;
     }
-    dz_template *t = nullptr;
-    int rc = dz_template_create(model, &t);
+    dz_options o;
+    if (opt)
+        o = *opt;
+    else
+        dz_options_default(&o);
+    std::lock_guard<std::mutex> lock(g_model_cache.mu);
+    // a cheap fingerprint of the structure; build_template validates the model on a miss and
+    // pack_theta re-checks the full structure hash on a hit
+    const int64_t T = (model->n_rows > 0 && model->row_ptr) ? model->row_ptr[model->n_rows] : 0;
+    ModelCacheEntry *hit = nullptr;
+    dz_template *probe = nullptr;
+    int rc = dz_template_create(model, &probe); // validates; the hash decides reuse
     if (rc != DZ_OK) return rc;
+    for (auto &e : g_model_cache.entries)
+        if (e.key == probe->host.structure_hash && e.n_vars == model->n_vars && e.n_obj == model->n_obj &&
+            e.n_rows == model->n_rows && e.n_terms == T && same_options(e.opt, o))
+            hit = &e;
+    if (hit) {
+        dz_template_destroy(probe);
+    } else {
+        dz_batch *nb = nullptr;
+        rc = dz_batch_create(probe, 1, &o, &nb);
+        if (rc != DZ_OK) {
+            dz_template_destroy(probe);
+            return rc;
+        }
+        if (g_model_cache.entries.size() >= kModelCacheEntries) {
+            size_t old = 0;
+            for (size_t i = 1; i < g_model_cache.entries.size(); ++i)
+                if (g_model_cache.entries[i].stamp < g_model_cache.entries[old].stamp) old = i;
+            dz_batch_destroy(g_model_cache.entries[old].b);
+            dz_template_destroy(g_model_cache.entries[old].t);
+            g_model_cache.entries.erase(g_model_cache.entries.begin() + (long)old);
+        }
+        ModelCacheEntry e;
+        e.key = probe->host.structure_hash;
+        e.n_vars = model->n_vars, e.n_obj = model->n_obj, e.n_rows = model->n_rows, e.n_terms = T;
+        e.opt = o;
+        e.t = probe;
+        e.b = nb;
+        g_model_cache.entries.push_back(e);
+        hit = &g_model_cache.entries.back();
+    }
+    hit->stamp = ++g_model_cache.clock;
+    dz_template *t = hit->t;
     std::vector<double> theta((size_t)t->host.n_theta);
     rc = dz::pack_theta(&t->host, model, theta.data(), &g_err);
-    if (rc != DZ_OK) {
-        dz_template_destroy(t);
-        return rc;
-    }
+    if (rc != DZ_OK) return rc;
     const size_t n_orig = t->host.orig_var.size();
     std::vector<double> vals(std::max<size_t>(n_orig, 1));
     int32_t status = 0, pivots = 0, n_primal = 0;
@@ -564,20 +689,29 @@ int dz_solve_model(const dz_model *model, const dz_options *opt, dz_solution *so
     r.trace_hash = &hash;
     r.objective = &objective;
     r.values = vals.data();
-    rc = dz_solve_batch(t, 1, theta.data(), opt, &r);
-    if (rc == DZ_OK) {
-        sol->status = status;
-        sol->pivots = pivots;
-        sol->n_primal = n_primal;
-        sol->trace_hash = hash;
-        sol->objective = objective;
-        if (values) {
-            for (int32_t v = 0; v < model->n_vars; ++v) values[v] = 0.0;
-            for (size_t k = 0; k < n_orig; ++k) values[t->host.orig_var[k]] = vals[k];
-        }
+    rc = dz_batch_upload(hit->b, theta.data());
+    if (rc == DZ_OK) rc = dz_batch_solve(hit->b);
+    if (rc == DZ_OK) rc = dz_batch_download(hit->b, &r); // synchronises: theta may go out of scope
+    if (rc != DZ_OK) { // keep nothing that may be in a bad state
+        for (size_t i = 0; i < g_model_cache.entries.size(); ++i)
+            if (&g_model_cache.entries[i] == hit) {
+                dz_batch_destroy(hit->b);
+                dz_template_destroy(hit->t);
+                g_model_cache.entries.erase(g_model_cache.entries.begin() + (long)i);
+                break;
+            }
+        return rc;
     }
-    dz_template_destroy(t);
-    return rc;
+    sol->status = status;
+    sol->pivots = pivots;
+    sol->n_primal = n_primal;
+    sol->trace_hash = hash;
+    sol->objective = objective;
+    if (values) {
+        for (int32_t v = 0; v < model->n_vars; ++v) values[v] = 0.0;
+        for (size_t k = 0; k < n_orig; ++k) values[t->host.orig_var[k]] = vals[k];
+    }
+    return DZ_OK;
 }
 
 const char *dz_last_error(void) { return g_err.c_str(); }

@@ -946,7 +946,7 @@ dz_core_kernel(const TemplateDev T, const BatchDev Bt, const int capW) {
             if (tid < 16) Bt.prof[(size_t)lp * 16 + tid] = c.prof[tid];
         }
         if (Bt.work) { // executed flop counts of this kernel's share of the LP
-            double *w = Bt.work + (size_t)lp * 4;
+            double *w = Bt.work + (size_t)lp * 8;
             if (c.n_lu) atomicAdd(&w[0], (double)c.n_lu);
             if (c.n_solve) atomicAdd(&w[1], (double)c.n_solve);
             if (c.n_price) atomicAdd(&w[2], (double)c.n_price);

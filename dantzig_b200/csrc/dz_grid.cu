@@ -58,6 +58,7 @@ struct G {
     double *sbuf;  // [kBufTerms]
     int parity;
     unsigned long long n_lu, n_solve, n_price;
+    unsigned long long stat_core, stat_real, stat_grid; // master: working-core doubles, steps, grid-wide steps
 };
 
 __device__ __forceinline__ void gsync(G &g, const GridDev &D) {
@@ -642,6 +643,7 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
                 D.pivr[cc] = pr;
             }
         }
+        g.stat_real += 1;
         if (pv != 0.0 && n_list > 1) {
             if (n_list <= 2 * g.NW) { // narrow step: the master's own warps, no grid barrier
                 __syncthreads();
@@ -653,6 +655,7 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
                     D.jobd[JD_0] = pv;
                 }
                 dispatch(g, D, T, Bt, J_UPDATE, k, cc, pr);
+                g.stat_grid += 1;
             }
             if (D.job[JI_EXOTIC] == 1) return false;
         }
@@ -813,6 +816,7 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
     g.S = 1;
     g.MW = 1;
     g.n_lu = g.n_solve = g.n_price = 0;
+    g.stat_core = g.stat_real = g.stat_grid = 0;
     {
         double *dp = reinterpret_cast<double *>(smem_raw);
         g.sbuf = dp, dp += kBufTerms;
@@ -845,6 +849,7 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
             unsigned long long hash = 0xcbf29ce484222325ULL, n_upd = 0;
             bool handed_over = false;
             long long dirty = 0; // doubles of W any solve of this LP has used
+            g.stat_core = g.stat_real = g.stat_grid = 0;
             while (true) {
                 // ---- status(), simplex.rs:274-306 ----
                 dispatch(g, D, T, Bt, J_STATUS);
@@ -911,6 +916,7 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
                         break;
                     }
                     dirty = max(dirty, (long long)nrow * g.S);
+                    g.stat_core += 2 * (unsigned long long)nrow * (unsigned long long)g.S; // two solves
                 }
                 dispatch(g, D, T, Bt, J_LISTS_WRITE);
                 int p = p0, q = q0;
@@ -1025,6 +1031,7 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
                 }
             } else {
                 dispatch(g, D, T, Bt, J_OBJ);
+                const unsigned long long core_doubles = g.stat_core, real_steps = g.stat_real, grid_steps = g.stat_grid;
                 if (tid == 0) {
                     const double *__restrict__ theta = Bt.theta + (size_t)lp * Bt.n_theta;
                     double obj = 0.0;
@@ -1035,7 +1042,13 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
                     Bt.n_primal[lp] = (int)n_primal;
                     Bt.trace_hash[lp] = hash;
                     Bt.objective[lp] = obj;
-                    if (Bt.work) atomicAdd(&Bt.work[(size_t)lp * 4 + 3], (double)n_upd);
+                    if (Bt.work) {
+                        double *w = Bt.work + (size_t)lp * 8;
+                        atomicAdd(&w[3], (double)n_upd);
+                        w[4] = (double)core_doubles;
+                        w[5] = (double)real_steps;
+                        w[6] = (double)grid_steps;
+                    }
                 }
             }
             __syncthreads();

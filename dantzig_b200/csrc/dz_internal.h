@@ -68,7 +68,7 @@ struct BatchDev {
     double *x_basic; // [B][M]
     int32_t *basis;  // [B][M]
     int32_t *trace;  // [B][trace_cap][3] or null
-    double *work;    // [B][4]
+    double *work;    // [B][8]
     long long *prof; // [B][16] per-phase cycles (optional, null = off)
     unsigned int *next_lp; // work-queue counter
     double *gws;     // global workspace for the basis when it does not fit in smem

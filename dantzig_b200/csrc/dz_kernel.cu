@@ -1380,7 +1380,7 @@ dz_batch_kernel(const TemplateDev T, const BatchDev Bt, const int smem_per_team)
         }
         if (Bt.work) {
             // per-LP executed flop counts (block sum via atomics on the output row)
-            double *w = Bt.work + (size_t)lp * 4;
+            double *w = Bt.work + (size_t)lp * 8;
             if (c.n_lu) atomicAdd(&w[0], (double)c.n_lu);
             if (c.n_solve) atomicAdd(&w[1], (double)c.n_solve);
             if (c.n_price) atomicAdd(&w[2], (double)c.n_price);

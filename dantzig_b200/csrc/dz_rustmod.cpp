@@ -66,6 +66,13 @@ struct LinExpr {
         return r;
     }
     LinExpr add(const LinExpr &o) const { // pyobjs.rs:78-104
+        // assert_eq!(coefs.len(), vars.len()); assert_eq!(coefs.len(), id_to_index.len()) (pyobjs.rs:83-84):
+        // mismatched lengths or duplicate variable ids on the left panic in the reference
+        if (coefs.size() != vars.size() || coefs.size() != id_to_index.size()) {
+            py::object exc = py::module_::import("dantzig.rust").attr("PanicException");
+            PyErr_SetString(exc.ptr(), "assertion failed: `(left == right)` (PyLinExpr.__add__, pyobjs.rs:83-84)");
+            throw py::error_already_set();
+        }
         LinExpr r(*this);
         for (std::size_t i = 0; i < o.coefs.size() && i < o.vars.size(); ++i) {
             auto it = r.id_to_index.find(o.vars[i].id);
@@ -127,6 +134,14 @@ struct Flat {
 };
 
 Flat flatten(const AffExpr &objective, const std::vector<Inequality> &constraints) {
+    // A PyLinExpr whose coefs and vars differ in length is malformed.  The reference zips
+    // them (model.rs:14) after registering every listed variable (simplex.rs:126-151), which
+    // leaves bound rows of variables that have no term; rather than guess at that, the
+    // drop-in refuses the model.
+    auto well_formed = [](const LinExpr &e) { return e.coefs.size() == e.vars.size(); };
+    bool ok = well_formed(objective.linexpr);
+    for (const auto &c : constraints) ok = ok && well_formed(c.linexpr);
+    if (!ok) throw py::value_error("PyLinExpr: coefs and vars differ in length");
     Flat f;
     const std::size_t n_obj = std::min(objective.linexpr.coefs.size(), objective.linexpr.vars.size());
     for (std::size_t i = 0; i < n_obj; ++i) {
@@ -230,7 +245,7 @@ Solution solve(const AffExpr &objective, const std::vector<Inequality> &constrai
 // result list holds, per LP and in input order, a PySolution or the exception
 // instance solve() would have raised (returned, not raised).
 py::list solve_batch(const std::vector<AffExpr> &objectives,
-                     const std::vector<std::vector<Inequality>> &constraints) {
+                     const std::vector<std::vector<Inequality>> &constraints, int n_gpus) {
     if (objectives.size() != constraints.size())
         throw py::value_error("solve_batch: objectives and constraints differ in length");
     const std::size_t n = objectives.size();
@@ -289,7 +304,10 @@ py::list solve_batch(const std::vector<AffExpr> &objectives,
                 r.trace_hash = th.data();
                 r.objective = ob.data();
                 r.values = vals.data();
-                rc = dz_solve_batch(t, (int64_t)B, theta.data(), &opt, &r);
+                // n_gpus == 1: this device; otherwise the group is sharded over n_gpus devices
+                // (0 = all visible), contiguous ranges, no collective (dz_solve_batch_multi)
+                rc = n_gpus == 1 ? dz_solve_batch(t, (int64_t)B, theta.data(), &opt, &r)
+                                 : dz_solve_batch_multi(t, (int64_t)B, theta.data(), n_gpus, &opt, &r);
             }
             if (rc != DZ_OK) failure = dz_last_error();
             dz_template_destroy(t);
@@ -383,5 +401,5 @@ PYBIND11_MODULE(rust, m) {
         });
 
     m.def("solve", &solve, py::arg("objective"), py::arg("constraints"));
-    m.def("solve_batch", &solve_batch, py::arg("objectives"), py::arg("constraints"));
+    m.def("solve_batch", &solve_batch, py::arg("objectives"), py::arg("constraints"), py::arg("n_gpus") = 1);
 }

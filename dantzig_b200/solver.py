@@ -92,7 +92,7 @@ class BatchResult:
     x_basic: np.ndarray | None
     basis: np.ndarray | None
     trace: np.ndarray | None
-    work: np.ndarray        # [B, 4] executed flops: LU, solves, pricing, updates
+    work: np.ndarray        # [B, 8] executed flops (LU, solves, pricing, updates) + kernel statistics
     prof: np.ndarray | None = None  # [B, 16] phase cycles (profile=True)
 
 
@@ -156,6 +156,12 @@ class Batch:
         _capi.check(_capi.lib().dz_batch_last_timing(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value)
 
+    def launches(self) -> int:
+        """Kernel launches of the last solve (2 when a hand-over launch follows the main one)."""
+        ms, n = C.c_float(), C.c_int32()
+        _capi.check(_capi.lib().dz_batch_last_timing(self._h, C.byref(ms), C.byref(n)))
+        return int(n.value)
+
     def launch_info(self) -> dict[str, int]:
         v = [C.c_int32() for _ in range(5)]
         _capi.check(_capi.lib().dz_batch_launch_info(self._h, *[C.byref(x) for x in v]))
@@ -178,7 +184,7 @@ class Batch:
             x_basic=None if light else np.zeros((B, t.m), np.float64),
             basis=None if light else np.zeros((B, t.m), np.int32),
             trace=None if (light or not self.trace_cap) else np.zeros((B, self.trace_cap, 3), np.int32),
-            work=np.zeros((B, 4), np.float64),
+            work=np.zeros((B, 8), np.float64),
             prof=np.zeros((B, 16), np.int64) if self.profile else None,
         )
         r = _capi.BatchResult()
@@ -189,6 +195,33 @@ class Batch:
         _capi.check(_capi.lib().dz_batch_download(self._h, C.byref(r)))
         res.values = res.values[:, : t.n_orig]
         return res
+
+
+def solve_batch_multi(template: Template, theta: np.ndarray, n_gpus: int = 0, *, max_pivots: int = 0,
+                      trace_cap: int = 0, light: bool = False, **kw) -> BatchResult:
+    """dz_solve_batch_multi: the batch sharded over the first ``n_gpus`` devices (0 = all),
+    contiguous LP ranges, one host thread and stream per device, no collective."""
+    theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, template.n_theta)
+    B, t = theta.shape[0], template
+    res = BatchResult(
+        status=np.zeros(B, np.int32), pivots=np.zeros(B, np.int32),
+        n_primal=np.zeros(B, np.int32), trace_hash=np.zeros(B, np.uint64),
+        objective=np.zeros(B, np.float64), values=np.zeros((B, max(t.n_orig, 1)), np.float64),
+        x_basic=None if light else np.zeros((B, t.m), np.float64),
+        basis=None if light else np.zeros((B, t.m), np.int32),
+        trace=None if (light or not trace_cap) else np.zeros((B, trace_cap, 3), np.int32),
+        work=np.zeros((B, 8), np.float64), prof=None,
+    )
+    r = _capi.BatchResult()
+    for name in ("status", "pivots", "n_primal", "trace_hash", "objective", "values",
+                 "x_basic", "basis", "trace", "work", "prof"):
+        a = getattr(res, name)
+        setattr(r, name, None if a is None else a.ctypes.data)
+    o = _options(0, max_pivots, trace_cap, kw.get("worker_warps", 0), kw.get("ctas_per_sm", 0), None, False,
+                 kw.get("basis_home", 0))
+    _capi.check(_capi.lib().dz_solve_batch_multi(t.handle, B, _vp(theta), int(n_gpus), C.byref(o), C.byref(r)))
+    res.values = res.values[:, : t.n_orig]
+    return res
 
 
 def solve_batch(template: Template, theta: np.ndarray, **kw) -> BatchResult:

@@ -151,7 +151,10 @@ typedef struct dz_batch_result {
     double *x_basic;      /* [B][m]      final x, position ordered                      */
     int32_t *basis;       /* [B][m]      final basic column per position                */
     int32_t *trace;       /* [B][trace_cap][3] (kind 0=primal 1=dual, leaving, entering)*/
-    double *work;         /* [B][4] executed flops: LU, solves, pricing, updates        */
+    double *work;         /* [B][8] executed flops: LU, solves, pricing, updates; then, from
+                             the single-LP kernel: doubles of working core cleared and
+                             filled over all solves, elimination steps that did arithmetic,
+                             of those the ones run grid-wide; one spare                  */
     int64_t *prof;        /* [B][16] SM cycles per phase + step counters (opt.profile)  */
 } dz_batch_result;
 
@@ -160,6 +163,14 @@ typedef struct dz_batch_result {
  * Copies theta to the device, runs the CTA-per-LP kernel, copies results back. */
 int dz_solve_batch(const dz_template *t, int64_t B, const double *theta, const dz_options *opt,
                    dz_batch_result *out);
+
+/* Same, sharded over the first n_gpus devices: device d takes the contiguous
+ * LP range [d*B/n_gpus, (d+1)*B/n_gpus), one host thread and one stream per device, no
+ * collective -- every shard's results land in its slice of `out`.  opt->device is ignored;
+ * n_gpus <= 0 means every visible device.  A single LP does not shard (its pivots are
+ * serially dependent): B < n_gpus simply leaves devices idle. */
+int dz_solve_batch_multi(const dz_template *t, int64_t B, const double *theta, int32_t n_gpus,
+                         const dz_options *opt, dz_batch_result *out);
 
 /* ---- device-resident batch (inputs stay in HBM across solves) -------------- */
 typedef struct dz_batch dz_batch;

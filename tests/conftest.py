@@ -40,3 +40,14 @@ def oracle():
 
     dzo_py.build()
     return dzo_py
+
+
+def reference_frontend_dir():
+    """Directory that holds the reference's unmodified `dantzig` Python package, or None:
+    $DANTZIG_FRONTEND, the reference checkout (this container), or the copy that
+    __graft_entry__.build() installs under baseline/_ref/ (what the GPU box has)."""
+    for cand in (os.environ.get("DANTZIG_FRONTEND"), "/root/reference/python-source",
+                 os.path.join(ROOT, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "dantzig", "optimize.py")):
+            return cand
+    return None

@@ -30,7 +30,7 @@ def _build(name="", flags=()):
 
 
 def _run(lib, *args):
-    env = dict(os.environ, DZ_LIB=lib)
+    env = dict(os.environ, DZ_LIB=lib, DZ_LIB_TEST_ONLY="1")
     r = subprocess.run([sys.executable, os.path.join(EMU, "run_child.py"), *args], env=env,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -89,7 +89,7 @@ def test_gpu_suite_subset_on_the_emulator():
     tests over whole fixtures are left to the GPU (minutes per shape here), and the
     dantzig.rust extension links the real library, so it is not part of this run."""
     lib = _build()
-    env = dict(os.environ, DZ_LIB=lib)
+    env = dict(os.environ, DZ_LIB=lib, DZ_LIB_TEST_ONLY="1")
     r = subprocess.run(
         [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q",
          "-x", "-p", "no:cacheprovider", "-k",

@@ -276,6 +276,24 @@ def test_full_config2_properties(oracle):
         assert np.abs(x - ref.x).max() <= 1e-7
 
 
+def test_solve_batch_multi(oracle):
+    """dz_solve_batch_multi: contiguous shards over the devices, no collective; the results
+    are those of the single-device entry, LP for LP.  With one visible device the sharding
+    logic still runs (n_gpus=1); with two or more the batch really splits."""
+    from dantzig_b200 import device_count, solve_batch_multi
+
+    w = generate.config2(203)                       # not a multiple of anything
+    t = Template(w.structure)
+    one = solve_batch(t, w.theta, trace_cap=16)
+    for n in sorted({1, min(2, device_count()), device_count()}):
+        r = solve_batch_multi(t, w.theta, n_gpus=n, trace_cap=16)
+        for name in ("status", "pivots", "n_primal", "trace_hash", "objective", "values", "x_basic", "basis", "trace"):
+            a, b = getattr(one, name), getattr(r, name)
+            assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f"), (n, name)
+    with pytest.raises(Exception):
+        solve_batch_multi(t, w.theta, n_gpus=device_count() + 1)
+
+
 def test_pivot_cap_is_reported():
     w = generate.config2(4)
     t = Template(w.structure)
@@ -374,13 +392,52 @@ def test_rust_module_solve_batch():
     assert rs.solve_batch([], []) == []
 
 
-def test_reference_python_tests_through_the_module():
-    """The reference's tests/test_optimize.py and tests/test_exceptions.py, driven
-    through the drop-in module with the call sequence the reference frontend makes
-    (tests/frontend_shim.py), solved on the GPU, asserted with exact ==."""
+def _real_frontend(rs):
+    """The reference's UNMODIFIED Python frontend (installed by __graft_entry__.build() under
+    baseline/_ref, or the checkout) on top of the drop-in module, wrapped to the same four
+    names the stand-in exposes."""
+    import importlib
+    import sys
+
+    from tests.conftest import reference_frontend_dir
+
+    ref = reference_frontend_dir()
+    if ref is None:
+        pytest.skip("reference frontend not present")
+    for k in [k for k in sys.modules if k == "dantzig" or k.startswith("dantzig.")]:
+        sys.modules.pop(k)
+    sys.modules["dantzig.rust"] = rs
+    sys.path.insert(0, ref)
+    try:
+        dz = importlib.import_module("dantzig")
+    finally:
+        sys.path.remove(ref)
+    assert os.path.dirname(dz.__file__).startswith(ref)
+    minimize = lambda obj, cs=(): dz.Minimize(obj).subject_to(list(cs)).solve()
+    maximize = lambda obj, cs=(): dz.Maximize(obj).subject_to(list(cs)).solve()
+    return dz.Variable, minimize, maximize, dz.exceptions
+
+
+@pytest.mark.parametrize("frontend", ["stand-in", "reference"])
+def test_reference_python_tests_through_the_module(frontend):
+    """The reference's tests/test_optimize.py and tests/test_exceptions.py, solved on the GPU
+    through the drop-in module, asserted with exact ==: once with the reference's own
+    unmodified frontend (dz.Minimize(...).subject_to(...).solve()), once with the stand-in
+    that makes the same call sequence (tests/frontend_shim.py)."""
+    import sys
+
     import dantzig_b200.rust as rs
 
-    Var, minimize, maximize, exc = _frontend(rs)
+    saved = {k: v for k, v in sys.modules.items() if k == "dantzig" or k.startswith("dantzig.")}
+    try:
+        _run_reference_cases(*(_real_frontend(rs) if frontend == "reference" else _frontend(rs)))
+    finally:
+        for k in [k for k in sys.modules if k == "dantzig" or k.startswith("dantzig.")]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)
+
+
+def _run_reference_cases(Var, minimize, maximize, exc):
     x, y = Var.nonneg(), Var.nonneg()                                    # test_problem_1
     s = minimize(2 * x - 2 * y, [y == 3])
     assert (s.objective_value, s[x], s[y]) == (-6.0, 0.0, 3.0)

@@ -6,7 +6,9 @@ import sys
 
 import pytest
 
-REF = "/root/reference/python-source"
+from tests.conftest import reference_frontend_dir
+
+REF = reference_frontend_dir()
 
 
 @pytest.fixture()
@@ -56,7 +58,7 @@ def test_solve_batch_host_side(rs):
             rs.solve_batch([obj], [[row]])
 
 
-@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+@pytest.mark.skipif(REF is None, reason="reference frontend not present (build() installs it under baseline/_ref)")
 def test_reference_frontend_expression_tests(rs):
     """tests/test_model.py of the reference, unmodified frontend on our module."""
     saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "dantzig" or k.startswith("dantzig.")}

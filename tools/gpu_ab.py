@@ -59,5 +59,5 @@ if __name__ == "__main__":
         child()
     else:
         for lib in sys.argv[1:]:
-            env = dict(os.environ, DZ_LIB=os.path.join(ROOT, lib))
+            env = dict(os.environ, DZ_LIB=os.path.join(ROOT, lib), DZ_LIB_TEST_ONLY="1")
             subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=env, check=False)

@@ -11,7 +11,7 @@ def run(name, t, theta, cap, lower_fn, check, **kw):
     b.upload(np.ascontiguousarray(theta).reshape(1, -1)); b.solve(); b.sync()
     r = b.download(light=True); ms = b.kernel_ms()
     msg = "%s lowered %dx%d cap %d %s launch %s: pivots %d status %d ms %.1f pivots/s %.1f Gflop %.2f" % (
-        name, t.m, t.n_int, cap, kw, b.launch_info(), r.pivots[0], r.status[0], ms, r.pivots[0] / ms * 1e3, r.work.sum() / 1e9)
+        name, t.m, t.n_int, cap, kw, b.launch_info(), r.pivots[0], r.status[0], ms, r.pivots[0] / ms * 1e3, r.work[:, :4].sum() / 1e9)
     b.close()
     if check:
         t0 = time.time()

@@ -32,7 +32,7 @@ def tput(name, w, **kw):
         best = min(best, b.kernel_ms())
     r = b.download(light=True)
     print("TPUT", name, kw, b.launch_info(), "ms %.1f LP/s %.0f" % (best, w.B / best * 1e3),
-          "status", np.bincount(r.status, minlength=5).tolist(), "Gflop exec %.2f" % (r.work.sum() / 1e9), flush=True)
+          "status", np.bincount(r.status, minlength=5).tolist(), "Gflop exec %.2f" % (r.work[:, :4].sum() / 1e9), flush=True)
     b.close()
 w2 = generate.config2(4096)
 for cps in (0, 2, 4):
