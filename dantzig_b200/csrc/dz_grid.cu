@@ -35,14 +35,26 @@ namespace {
 
 enum {
     J_EXIT = 0, J_INIT, J_INIT2, J_STATUS, J_LISTS_COUNT, J_LISTS_WRITE, J_ZERO, J_SCATTER, J_UPDATE,
-    J_BACK_PREP, J_YSCATTER, J_PRICE, J_RATIO, J_VECUPD, J_OBJ
+    J_BACK_PREP, J_YSCATTER, J_PRICE, J_RATIO, J_VECUPD, J_OBJ, J_EPOCH_A, J_EPOCH_B, J_BACKSUB
 };
 // job descriptor words (ints) and doubles
-enum { JI_TYPE = 0, JI_A0, JI_A1, JI_A2, JI_A3, JI_A4, JI_NR, JI_EXOTIC, JI_NLIST, JI_WORDS = 16 };
+enum { JI_TYPE = 0, JI_A0, JI_A1, JI_A2, JI_A3, JI_A4, JI_NR, JI_EXOTIC, JI_NLIST, JI_NCOLS, JI_NWORDS, JI_CURSOR, JI_WORDS = 16 };
 enum { JD_0 = 0, JD_1, JD_2, JD_3, JD_WORDS = 8 };
 constexpr int kBufTerms = 2048; // ordered products of one back-substitution row per round (shared memory)
+#ifndef DZ_GRID_HEAP_CAP
+#define DZ_GRID_HEAP_CAP 4096 // tests shrink it to exercise the overflow path
+#endif
+constexpr int kHeapCap = DZ_GRID_HEAP_CAP; // positions disturbed by interchanges, waiting for their step (master, shared memory)
+constexpr int kWin = 64;      // core columns per look-ahead window of the transposed elimination
+constexpr int kWarpBuf = kBufTerms / 16; // ... per warp in the grid-wide back-substitution (16 warps per CTA)
+
+// Slots of the optional cycle profile of the master CTA (BatchDev::prof, 16 per LP).
+enum { GP_STATUS = 0, GP_LISTS, GP_ZERO_SCATTER, GP_BOOK_FAST, GP_SEARCH, GP_UPDATE, GP_EPOCH, GP_BACK_PREP, GP_BACK_CHAIN,
+       GP_PRICE, GP_RATIO, GP_VECUPD, GP_FAST_COMMITS, GP_SLOW_STEPS, GP_EPOCHS, GP_PENDING_ROWS };
 
 struct G {
+    long long *prof; // shared memory of the master, or null
+    long long t_last;
     // geometry
     int M, Nn, NT, NW, tid, lane, warp, nblocks, blk;
     long long gtid, GT;
@@ -56,8 +68,12 @@ struct G {
     int *scan;
     int *sctl;
     double *sbuf;  // [kBufTerms]
+    unsigned long long *wmax; // [kWin] window: column maxima as bit patterns
+    int *wcnt, *wcand;        // [kWin], [4 kWin]: rows attaining them
+    int *heap;                // [kHeapCap] min-heap of disturbed positions; size in sctl[10], overflow in sctl[11]
     int parity;
     unsigned long long n_lu, n_solve, n_price;
+    int nse[2]; // entries of the exceptional-position lists seu / set of this basis
     unsigned long long stat_core, stat_real, stat_grid; // master: working-core doubles, steps, grid-wide steps
 };
 
@@ -84,63 +100,57 @@ __device__ __forceinline__ void gsync(G &g, const GridDev &D) {
 #endif
 }
 
+__device__ __forceinline__ void gtick(G &g, int slot) {
+    if (g.prof && g.tid == 0) {
+        const long long now = clock64();
+        g.prof[slot] += now - g.t_last;
+        g.t_last = now;
+    }
+}
+__device__ __forceinline__ void gcount(G &g, int slot, long long n) {
+    if (g.prof && g.tid == 0) g.prof[slot] += n;
+}
+
 __device__ __forceinline__ double fast_div(double v, double pv) {
     return (pv == 1.0) ? v : ((pv == -1.0) ? -v : __ddiv_rn(v, pv));
 }
 
 // Elimination update of the candidate rows list[first], list[first + stride], ... (one warp
 // per row): l = a_ik / pivot, then a_ij -= l * a_kj over the nonzero pattern of the pivot row
-// right of the pivot column, the right-hand side included (linalg.rs:118-124, :288-290).
-__device__ __forceinline__ void update_rows(G &g, const GridDev &D, int first, int stride, int n_list, int k, int cc, int pr,
-                                            double pv) {
+// right of the pivot column, the right-hand side included (linalg.rs:118-124, :288-290).  The
+// pivot row arrives compacted by the master: its nonzero-pattern columns and values (pcols,
+// pvals: ncols entries, any order -- the element updates of one step are independent) and the
+// mask words that hold them (pwq, pwb: nwords entries).
+__device__ __forceinline__ void update_rows(G &g, const GridDev &D, int first, int stride, int n_list, int cc,
+                                            int pr, double pv, int ncols, int nwords) {
     const int nr = g.nr, MW = g.MW, lane = g.lane;
     const long long S = g.S;
-    const double *__restrict__ prow = D.W + (size_t)pr * S;
-    const unsigned *__restrict__ pmask = D.rmask + (size_t)pr * MW;
-    const double urhs = prow[nr];
-    const int q0 = (cc + 1) >> 5;
+    const double urhs = D.W[(size_t)pr * S + nr];
     bool bad = !isfinite(urhs);
     for (int e = first; e < n_list; e += stride) {
         const int i = D.list[e];
         if (i == pr) continue;
         double *__restrict__ row = D.W + (size_t)i * S;
         unsigned *__restrict__ imask = D.rmask + (size_t)i * MW;
-        const double v = row[cc];
-        const double l = fast_div(v, pv);
+        const double l = fast_div(row[cc], pv);
         bad = bad || !isfinite(l);
-        unsigned long long cnt = 0;
-        for (int wb = q0; wb < MW; wb += 32) {
-            const int q = wb + lane;
-            unsigned word = (q < MW) ? pmask[q] : 0u;
-            if (q == q0) {
-                const int lo = cc + 1 - 32 * q0;
-                word = lo >= 32 ? 0u : (word & ~((1u << lo) - 1u));
-            }
-            if (word && q < MW) imask[q] |= word; // fill pattern
-            unsigned nzw = __ballot_sync(kFull, word != 0u);
-            while (nzw) {
-                const int wq = __ffs(nzw) - 1;
-                nzw &= nzw - 1;
-                const unsigned bits = __shfl_sync(kFull, word, wq);
-                if ((bits >> lane) & 1u) {
-                    const int j = 32 * (wb + wq) + lane;
-                    const double u = prow[j];
-                    bad = bad || !isfinite(u);
-                    row[j] = __dsub_rn(row[j], __dmul_rn(l, u));
-                }
-                cnt += 2ull * __popc(bits);
-            }
+#pragma unroll 4
+        for (int t = lane; t < ncols; t += 32) {
+            const int j = D.pcols[t];
+            row[j] = __dsub_rn(row[j], __dmul_rn(l, D.pvals[t]));
         }
+        for (int t = lane; t < nwords; t += 32) imask[D.pwq[t]] |= D.pwb[t]; // fill pattern
         if (lane == 0) {
+            if (ncols > 0) D.rlast[i] = max(D.rlast[i], D.rlast[pr]);
+            unsigned long long cnt = 2ull * ncols + 1;
             if (urhs != 0.0) {
                 row[nr] = __dsub_rn(row[nr], __dmul_rn(l, urhs));
                 cnt += 2;
             }
-            g.n_lu += cnt + 1;
+            g.n_lu += cnt;
         }
     }
     if (__ballot_sync(kFull, bad) && lane == 0) D.job[JI_EXOTIC] = 1;
-    (void)k;
 }
 
 // Every wide phase, executed by all CTAs between two grid barriers.
@@ -244,54 +254,61 @@ __device__ __forceinline__ void exec_job(G &g, const GridDev &D, const TemplateD
     }
     case J_LISTS_COUNT:
     case J_LISTS_WRITE: {
-        // The coupled core (see dz_core.cu core_lists): CTA b owns the index range [b*chunk,
-        // (b+1)*chunk), so that the concatenation of the CTAs' lists is in index order.
+        // Four ordered lists of indices in [0, M), built in one pass (CTA b owns the range
+        // [b*chunk, (b+1)*chunk), so the concatenation of the CTAs' pieces is in index order):
+        //   0  core rows: constraint rows a structural basis column touches   (rmapR, rlist)
+        //   1  core positions: structural, or the slack of a core row          (pmap, plist)
+        //   2  positions whose elimination step in B is not a no-op from the start: anything but
+        //      "the slack of row p sits at position p"                         (seu)
+        //   3  the same for B^T, whose columns are the constraint rows          (set)
         const int chunk = (M + g.nblocks - 1) / g.nblocks;
         const int lo = g.blk * chunk, hi = min(M, lo + chunk);
         const unsigned lt = (1u << g.lane) - 1u;
-        int offr = type == J_LISTS_WRITE ? D.bcnt[2 * g.nblocks + g.blk] : 0;
-        int offc = type == J_LISTS_WRITE ? D.bcnt[3 * g.nblocks + g.blk] : 0;
-        int nrow = 0, ncol = 0;
+        int off[4], tot[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) off[q] = type == J_LISTS_WRITE ? D.bcnt[(4 + q) * g.nblocks + g.blk] : 0;
         for (int base = lo; base < hi; base += g.NT) {
             const int i = base + g.tid;
-            bool pr = false, pc = false;
+            bool pr[4] = {false, false, false, false};
             if (i < hi) {
-                pr = D.rowcnt[i] > 0;
-                const int sr = D.srow[i];
-                pc = sr < 0 || D.rowcnt[sr] > 0;
+                const int rc = D.rowcnt[i], sr = D.srow[i];
+                pr[0] = rc > 0;
+                pr[1] = sr < 0 || D.rowcnt[sr] > 0;
+                pr[2] = sr != i;
+                pr[3] = rc > 0 || D.spos[i] != i;
             }
-            const unsigned mr = __ballot_sync(kFull, pr), mc = __ballot_sync(kFull, pc);
-            if (g.lane == 0) {
-                g.scan[g.warp] = __popc(mr);
-                g.scan[kMaxWarps + g.warp] = __popc(mc);
+            unsigned mk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                mk[q] = __ballot_sync(kFull, pr[q]);
+                if (g.lane == 0) g.scan[q * kMaxWarps + g.warp] = __popc(mk[q]);
             }
             __syncthreads();
-            int wr = 0, wc = 0, tr = 0, tc = 0;
-            for (int w = 0; w < g.NW; ++w) {
-                const int a = g.scan[w], b = g.scan[kMaxWarps + w];
-                if (w < g.warp) {
-                    wr += a;
-                    wc += b;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int before = 0, all = 0;
+                for (int w = 0; w < g.NW; ++w) {
+                    const int a = g.scan[q * kMaxWarps + w];
+                    if (w < g.warp) before += a;
+                    all += a;
                 }
-                tr += a;
-                tc += b;
+                if (type == J_LISTS_WRITE && i < hi) {
+                    const int at = pr[q] ? off[q] + tot[q] + before + __popc(mk[q] & lt) : -1;
+                    if (q == 0) {
+                        D.rmapR[i] = at;
+                        if (pr[q]) D.rlist[at] = i;
+                    } else if (q == 1) {
+                        D.pmap[i] = at;
+                        if (pr[q]) D.plist[at] = i;
+                    } else if (pr[q]) {
+                        (q == 2 ? D.seu : D.set_)[at] = i;
+                    }
+                }
+                tot[q] += all;
             }
-            if (type == J_LISTS_WRITE && i < hi) {
-                const int ir = pr ? offr + nrow + wr + __popc(mr & lt) : -1;
-                D.rmapR[i] = ir;
-                if (pr) D.rlist[ir] = i;
-                const int ic = pc ? offc + ncol + wc + __popc(mc & lt) : -1;
-                D.pmap[i] = ic;
-                if (pc) D.plist[ic] = i;
-            }
-            nrow += tr;
-            ncol += tc;
             __syncthreads();
         }
-        if (type == J_LISTS_COUNT && g.tid == 0) {
-            D.bcnt[g.blk] = nrow;
-            D.bcnt[g.nblocks + g.blk] = ncol;
-        }
+        if (type == J_LISTS_COUNT && g.tid < 4) D.bcnt[g.tid * g.nblocks + g.blk] = tot[g.tid];
         break;
     }
     case J_ZERO: { // a0 = rows of W and of rmask to clear; also the tables of a fresh elimination
@@ -300,6 +317,10 @@ __device__ __forceinline__ void exec_job(G &g, const GridDev &D, const TemplateD
         const long long nm = a2 ? 0 : (long long)a0 * g.MW;
         for (long long e = g.gtid; e < nw; e += g.GT) D.W[e] = 0.0;
         for (long long e = g.gtid; e < nm; e += g.GT) D.rmask[e] = 0u;
+        for (long long e = g.gtid; e < a0; e += g.GT) {
+            D.rlast[e] = -1;
+            D.done[e] = 0;
+        }
         double *y = a1 ? D.vv : D.dxv;
         for (long long i = g.gtid; i < M; i += g.GT) {
             D.rowAt[i] = (int)i;
@@ -316,6 +337,11 @@ __device__ __forceinline__ void exec_job(G &g, const GridDev &D, const TemplateD
         double *y = transposed ? D.vv : D.dxv;
         for (int cc = g.gwarp; cc < nr; cc += g.GW) {
             const int col = D.bas[D.plist[cc]];
+            if (!transposed && g.lane == 0) { // a slack column of the core is its row's pivot column unless
+                                              // the row is used up before (then its step says otherwise)
+                const int sr = D.srow[D.plist[cc]];
+                if (sr >= 0) D.pivr[cc] = D.rmapR[sr];
+            }
             for (int e = T.col_ptr[col] + g.lane; e < T.col_ptr[col + 1]; e += 32) {
                 const double val = D.lval[e];
                 if (val == 0.0) continue; // exact zeros are not stored (linalg.rs:261)
@@ -323,6 +349,7 @@ __device__ __forceinline__ void exec_job(G &g, const GridDev &D, const TemplateD
                 const int wi = transposed ? cc : ir, wj = transposed ? ir : cc;
                 D.W[(size_t)wi * S + wj] = val;
                 atomicOr(&D.rmask[(size_t)wi * MW + (wj >> 5)], 1u << (wj & 31));
+                atomicMax(&D.rlast[wi], wj);
             }
         }
         if (transposed) {
@@ -348,8 +375,54 @@ __device__ __forceinline__ void exec_job(G &g, const GridDev &D, const TemplateD
         break;
     }
     case J_UPDATE:
-        update_rows(g, D, g.gwarp, g.GW, D.job[JI_NLIST], a0, a1, a2, D.jobd[JD_0]);
+        update_rows(g, D, g.gwarp, g.GW, D.job[JI_NLIST], a1, a2, D.jobd[JD_0], D.job[JI_NCOLS], D.job[JI_NWORDS]);
         break;
+    case J_EPOCH_A:
+    case J_EPOCH_B: {
+        // Column maxima of the remaining core columns [a0, nr) over the rows at positions >= a1,
+        // for the run of steps that follows without any change to W (see grid_solve):
+        // A: colmax[j] = max |a_ij| as a bit pattern; B: up to four rows that attain it.
+        const int nr = g.nr, MW = g.MW, from = a0, kmin = a1;
+        const long long S = g.S;
+        const int *rl = D.job[JI_A2] ? D.plist : D.rlist;
+        bool bad = false;
+        for (int i = g.gwarp; i < nr; i += g.GW) {
+            if (D.posOf[rl[i]] < kmin) continue;
+            const double *__restrict__ row = D.W + (size_t)i * S;
+            const unsigned *__restrict__ mask = D.rmask + (size_t)i * MW;
+            const int q0 = from >> 5;
+            for (int wb = q0; wb < MW; wb += 32) {
+                const int q = wb + g.lane;
+                unsigned word = (q < MW) ? mask[q] : 0u;
+                if (q == q0) {
+                    const int lo = from - 32 * q0;
+                    word = word & ~((1u << lo) - 1u);
+                }
+                unsigned nzw = __ballot_sync(kFull, word != 0u);
+                while (nzw) {
+                    const int wq = __ffs(nzw) - 1;
+                    nzw &= nzw - 1;
+                    const unsigned bits = __shfl_sync(kFull, word, wq);
+                    if ((bits >> g.lane) & 1u) {
+                        const int j = 32 * (wb + wq) + g.lane;
+                        const double v = row[j];
+                        bad = bad || !isfinite(v);
+                        const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(v));
+                        if (v != 0.0) {
+                            if (type == J_EPOCH_A) {
+                                atomicMax(&D.colmax[j], key);
+                            } else if (key == D.colmax[j]) {
+                                const int slot = atomicAdd(&D.colcnt[j], 1);
+                                if (slot < 4) D.colcand[4 * j + slot] = i;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(kFull, bad) && g.lane == 0) D.job[JI_EXOTIC] = 1;
+        break;
+    }
     case J_BACK_PREP: {
         // rows whose strict upper part is empty are solved at once (x/1 == x); the others are
         // left to the master's ordered chains.  pend[cc] = 1 marks them.
@@ -376,10 +449,103 @@ __device__ __forceinline__ void exec_job(G &g, const GridDev &D, const TemplateD
                     const double d = row[cc], s = row[nr];
                     const double yi = (d == 1.0) ? s : __ddiv_rn(s, d);
                     D.ycore[cc] = yi;
+                    D.done[cc] = 1;
                     if (!isfinite(yi)) D.job[JI_EXOTIC] = 2; // non-finite component: see the master
                     g.n_solve += 1;
                 }
             }
+        }
+        break;
+    }
+    case J_BACKSUB: {
+        // Back substitution (linalg.rs:292-297) of the rows the prep job left, LEVEL-SCHEDULED by
+        // data flow: every warp of the grid takes core columns in descending order from a shared
+        // cursor and waits, entry by entry of its row's pattern, for the components it needs
+        // (done[j]); rows that do not depend on each other proceed side by side.  A row's
+        // products u_ij * y_j are formed by the lanes, staged in column order in the warp's slice
+        // of shared memory and subtracted one after the other (ascending j, linalg.rs:294).
+        const int nr = g.nr, MW = g.MW, lane = g.lane;
+        const long long S = g.S;
+        double *buf = g.sbuf + (size_t)g.warp * kWarpBuf;
+        const unsigned lt = (1u << lane) - 1u;
+        for (;;) {
+            int idx = 0;
+            if (lane == 0) idx = atomicAdd(&D.job[JI_CURSOR], 1);
+            idx = __shfl_sync(kFull, idx, 0);
+            if (idx >= nr) break;
+            const int cc = nr - 1 - idx;
+            if (!D.pend[cc]) continue;
+            const int i = D.pivr[cc];
+            const double *__restrict__ row = D.W + (size_t)i * S;
+            const unsigned *__restrict__ mask = D.rmask + (size_t)i * MW;
+            double s = row[nr];
+            const double d = row[cc];
+            const int q0 = (cc + 1) >> 5;
+            int nbuf = 0;
+            unsigned long long ops = 0;
+            for (int wb = q0; wb < MW; wb += 32) {
+                const int q = wb + lane;
+                unsigned word = (q < MW) ? mask[q] : 0u;
+                if (q == q0) {
+                    const int lo = cc + 1 - 32 * q0;
+                    word = lo >= 32 ? 0u : (word & ~((1u << lo) - 1u));
+                }
+                unsigned nzw = __ballot_sync(kFull, word != 0u);
+                while (nzw) {
+                    const int wq = __ffs(nzw) - 1;
+                    nzw &= nzw - 1;
+                    const unsigned bits = __shfl_sync(kFull, word, wq);
+                    const bool has = (bits >> lane) & 1u;
+                    const int j = 32 * (wb + wq) + lane;
+                    for (;;) { // wait for the components this group of columns needs
+                        const bool ok = !has || *((volatile int *)&D.done[j]) != 0;
+                        if (__ballot_sync(kFull, !ok) == 0u) break;
+#ifdef DZ_EMU
+                        emu::yield();
+#endif
+                    }
+                    __threadfence();
+                    double p = 0.0;
+                    if (has) {
+#ifdef DZ_EMU
+                        const double yj = D.ycore[j];
+#else
+                        const double yj = __ldcg(&D.ycore[j]);
+#endif
+                        p = __dmul_rn(row[j], yj);
+                    }
+                    const bool take = has && p != 0.0; // subtracting an exact zero changes nothing
+                    const unsigned mk = __ballot_sync(kFull, take);
+                    if (nbuf + __popc(mk) > kWarpBuf) { // flush the staged products, in order
+                        __syncwarp();
+                        for (int t = 0; t < nbuf; ++t) s = __dsub_rn(s, buf[t]);
+                        ops += 2ull * nbuf;
+                        nbuf = 0;
+                        __syncwarp();
+                    }
+                    if (take) buf[nbuf + __popc(mk & lt)] = p;
+                    nbuf += __popc(mk);
+                }
+            }
+            __syncwarp();
+            {
+                int t = 0;
+                for (; t + 4 <= nbuf; t += 4) {
+                    const double p0 = buf[t], p1 = buf[t + 1], p2 = buf[t + 2], p3 = buf[t + 3];
+                    s = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(s, p0), p1), p2), p3);
+                }
+                for (; t < nbuf; ++t) s = __dsub_rn(s, buf[t]);
+                ops += 2ull * nbuf + 1;
+            }
+            const double yi = (d == 1.0) ? s : __ddiv_rn(s, d);
+            if (lane == 0) {
+                D.ycore[cc] = yi;
+                __threadfence();
+                atomicExch((unsigned *)&D.done[cc], 1u);
+                if (!isfinite(yi)) D.job[JI_EXOTIC] = 2;
+                g.n_solve += ops;
+            }
+            __syncwarp();
         }
         break;
     }
@@ -501,12 +667,49 @@ __device__ __noinline__ void dispatch(G &g, const GridDev &D, const TemplateDev 
     }
 }
 
-__device__ __forceinline__ void g_swap_pos(const GridDev &D, int k, int mu) {
+// min-heap of positions an interchange has disturbed (one thread: lane 0 of the control warp)
+__device__ __forceinline__ void heap_push(G &g, int v) {
+    int n = g.sctl[10];
+    if (n >= kHeapCap) {
+        g.sctl[11] = 1; // overflow: the control warp goes back to scanning every position
+        return;
+    }
+    int i = n++;
+    while (i > 0) {
+        const int p = (i - 1) >> 1;
+        const int pv = g.heap[p];
+        if (pv <= v) break;
+        g.heap[i] = pv;
+        i = p;
+    }
+    g.heap[i] = v;
+    g.sctl[10] = n;
+}
+__device__ __forceinline__ void heap_pop(G &g) {
+    int n = g.sctl[10] - 1;
+    g.sctl[10] = n;
+    if (n <= 0) return;
+    const int v = g.heap[n];
+    int i = 0;
+    for (;;) {
+        int c = 2 * i + 1;
+        if (c >= n) break;
+        if (c + 1 < n && g.heap[c + 1] < g.heap[c]) ++c;
+        if (g.heap[c] >= v) break;
+        g.heap[i] = g.heap[c];
+        i = c;
+    }
+    g.heap[i] = v;
+}
+
+__device__ __forceinline__ void g_swap_pos(G &g, const GridDev &D, int k, int mu) {
+    if (mu == k) return;
     const int rk = D.rowAt[k], rm = D.rowAt[mu];
     D.rowAt[k] = rm;
     D.rowAt[mu] = rk;
     D.posOf[rm] = k;
     D.posOf[rk] = mu;
+    heap_push(g, mu); // position mu no longer holds what its step expects
 }
 
 // master: reduce the per-CTA partial arg-max results of J_STATUS / J_RATIO (slot n)
@@ -541,44 +744,127 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
     (void)lp;
     if (tid == 0) {
         D.job[JI_EXOTIC] = 0;
-        D.job[14] = (int)S;  // workers recompute S and MW from nr; kept for debugging
+        g.sctl[10] = 0; // heap of disturbed positions: empty
+        g.sctl[11] = 0; // ... not overflowed
     }
     dispatch(g, D, T, Bt, J_ZERO, nr, transposed ? 1 : 0);
     dispatch(g, D, T, Bt, J_SCATTER, transposed ? 1 : 0, arg);
+    gtick(g, GP_ZERO_SCATTER);
 
     // ---- elimination (master; dense steps go to the grid) ----
+    // WINDOWS.  In the transposed system nearly every core column is won by a row that has
+    // nothing right of the pivot (the slack's row of B^T) and a zero right-hand side: such a
+    // step records an interchange and changes no value.  So while W does not change, the
+    // master finds the column maxima of the next kWin core columns at once (its threads walk
+    // the rows' masks; maxima, tie counts and up to four tied rows per column go to shared
+    // memory), and the control warp then commits step after step from them -- checking that
+    // the stored candidates are still there and breaking ties by their CURRENT positions --
+    // without a search and without a CTA barrier.  A step that changes W ends the window.
     int k = 0;
+    bool epoch_valid = false;
+    int epoch_lo = 0, epoch_hi = 0;
+    int cc_next = 0, cooldown = 0; // transposed: core columns are real steps, in order
+    int sp = 0;                    // cursor in the exceptional-position list (control warp)
     for (;;) {
-        if (warp == 0) {
-            int irregular = 0;
-            for (;;) { // bookkeeping steps, see dz_core.cu
-                const int kk = k + lane;
-                bool noop = false;
-                if (kk < M - 1) {
-                    const int cc = cmap[kk];
-                    const int u = transposed ? (cc < 0 ? D.spos[kk] : -1) : D.srow[kk];
-                    noop = u >= 0 && D.rowAt[kk] == u;
-                    if (noop && cc >= 0) D.pivr[cc] = rmap[u];
+        if (transposed && !epoch_valid && cooldown == 0 && nr - cc_next >= 8) {
+            epoch_lo = cc_next;
+            epoch_hi = min(nr, cc_next + kWin);
+            if (tid < kWin) {
+                g.wmax[tid] = 0ull;
+                g.wcnt[tid] = 0;
+            }
+            if (tid == 0) g.sctl[8] = 0; // fast commits of this window
+            __syncthreads();
+            const int qa = epoch_lo >> 5, qb = (epoch_hi - 1) >> 5;
+            bool wbad = false;
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int i = tid; i < nr; i += g.NT) {
+                    if (D.posOf[rlist[i]] < k) continue;
+                    const double *__restrict__ row = D.W + (size_t)i * S;
+                    const unsigned *__restrict__ mask = D.rmask + (size_t)i * MW;
+                    for (int q = qa; q <= qb; ++q) {
+                        unsigned word = mask[q];
+                        while (word) {
+                            const int bbit = __ffs(word) - 1;
+                            word &= word - 1;
+                            const int j = 32 * q + bbit;
+                            if (j < epoch_lo || j >= epoch_hi) continue;
+                            const double v = row[j];
+                            wbad = wbad || !isfinite(v);
+                            if (v == 0.0) continue;
+                            const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(v));
+                            if (pass == 0) {
+                                atomicMax(&g.wmax[j - epoch_lo], key);
+                            } else if (key == g.wmax[j - epoch_lo]) {
+                                const int slot = atomicAdd(&g.wcnt[j - epoch_lo], 1);
+                                if (slot < 4) g.wcand[4 * (j - epoch_lo) + slot] = i;
+                            }
+                        }
+                    }
                 }
-                const unsigned m = __ballot_sync(kFull, noop);
-                const int run = (m == kFull) ? 32 : __ffs(~m) - 1;
-                k += run;
-                if (run == 32) continue;
-                if (k >= M - 1) break;
+                __syncthreads();
+            }
+            if (wbad) g.sctl[1] = 1;
+            __syncthreads();
+            if (g.sctl[1]) return false;
+            epoch_valid = true;
+            gtick(g, GP_EPOCH);
+            gcount(g, GP_EPOCHS, 1);
+        }
+        if (warp == 0) {
+            int irregular = 0, need_refresh = 0;
+            const int *__restrict__ se = transposed ? D.set_ : D.seu;
+            const int nse = g.nse[transposed ? 1 : 0];
+            for (;;) { // bookkeeping steps, see dz_core.cu
+                if (!g.sctl[11]) {
+                    // JUMP to the next position whose step is not known to be a no-op: the next
+                    // entry of this basis's exceptional list, or the smallest position an
+                    // interchange of this elimination has disturbed (heap), whichever comes first
+                    int nk = 0;
+                    if (lane == 0) {
+                        while (sp < nse && se[sp] < k) ++sp;
+                        const int a = sp < nse ? se[sp] : M;
+                        while (g.sctl[10] > 0 && g.heap[0] < k) heap_pop(g);
+                        const int b = g.sctl[10] > 0 ? g.heap[0] : M;
+                        nk = min(a, b);
+                    }
+                    nk = __shfl_sync(kFull, nk, 0);
+                    sp = __shfl_sync(kFull, sp, 0);
+                    k = min(nk, M - 1);
+                    if (k >= M - 1) break;
+                } else {
+                    // (heap overflow) every position, a run of no-ops 32 at a time
+                    const int kk = k + lane;
+                    bool noop = false;
+                    if (kk < M - 1) {
+                        const int cc = cmap[kk];
+                        const int u = transposed ? (cc < 0 ? D.spos[kk] : -1) : D.srow[kk];
+                        noop = u >= 0 && D.rowAt[kk] == u;
+                        if (noop && cc >= 0) D.pivr[cc] = rmap[u];
+                    }
+                    const unsigned m = __ballot_sync(kFull, noop);
+                    const int run = (m == kFull) ? 32 : __ffs(~m) - 1;
+                    k += run;
+                    if (run == 32) continue;
+                    if (k >= M - 1) break;
+                }
                 int adv = 0;
                 if (lane == 0) {
                     const int cc = cmap[k];
                     const int u = transposed ? (cc < 0 ? D.spos[k] : -1) : D.srow[k];
-                    if (cc < 0) {
+                    if (u >= 0 && D.rowAt[k] == u) { // a no-op after all
+                        if (cc >= 0) D.pivr[cc] = rmap[u];
+                        adv = 1;
+                    } else if (cc < 0) {
                         const int pu = u >= 0 ? D.posOf[u] : -1;
                         if (pu < k) {
                             irregular = 1;
                         } else {
-                            g_swap_pos(D, k, pu);
+                            g_swap_pos(g, D, k, pu);
                             adv = 1;
                         }
                     } else if (u >= 0 && D.posOf[u] >= k) {
-                        g_swap_pos(D, k, D.posOf[u]);
+                        g_swap_pos(g, D, k, D.posOf[u]);
                         D.pivr[cc] = rmap[u];
                         adv = 1;
                     }
@@ -586,6 +872,37 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
                 adv = __shfl_sync(kFull, adv, 0);
                 irregular = __shfl_sync(kFull, irregular, 0);
                 __syncwarp();
+                if (!adv && !irregular && epoch_valid) {
+                    // a real step: commit it from the window's column maxima if it changes nothing
+                    const int cc = cmap[k];
+                    if (cc >= epoch_hi) {
+                        need_refresh = 1; // window used up: the next one is computed before going on
+                    } else if (cc >= epoch_lo) {
+                        const int cnt = g.wcnt[cc - epoch_lo];
+                        if (cnt >= 1 && cnt <= 4) {
+                            const int row = lane < cnt ? g.wcand[4 * (cc - epoch_lo) + lane] : -1;
+                            int pos = row >= 0 ? D.posOf[rlist[row]] : 0x7fffffff;
+                            if (pos < k) pos = 0x7fffffff; // that candidate has been used up since
+                            const int best = __reduce_min_sync(kFull, pos);
+                            if (best != 0x7fffffff) {
+                                const int src = __ffs(__ballot_sync(kFull, pos == best)) - 1;
+                                const int pr = __shfl_sync(kFull, row, src);
+                                const bool inert = D.rlast[pr] <= cc && D.W[(size_t)pr * S + nr] == 0.0;
+                                if (inert) {
+                                    if (lane == 0) {
+                                        g_swap_pos(g, D, k, best); // linalg.rs:107-114
+                                        D.pivr[cc] = pr;
+                                        g.sctl[8] += 1;
+                                        if (g.prof) g.prof[GP_FAST_COMMITS] += 1;
+                                    }
+                                    adv = 1;
+                                    ++cc_next;
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
                 if (!adv) break;
                 ++k;
             }
@@ -593,12 +910,21 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
                 g.sctl[0] = k;
                 g.sctl[1] = irregular;
                 g.sctl[2] = 0; // candidate rows with a nonzero in the pivot column
+                g.sctl[7] = cc_next;
+                g.sctl[9] = need_refresh;
             }
         }
         __syncthreads();
+        gtick(g, GP_BOOK_FAST);
         k = g.sctl[0];
+        cc_next = g.sctl[7];
         if (g.sctl[1]) return false;
         if (k >= M - 1) break;
+        if (g.sctl[9]) { // the window is used up
+            epoch_valid = false;
+            __syncthreads();
+            continue;
+        }
         // pivot search in core column cc over the rows at positions >= k (linalg.rs:98-105):
         // largest |a_ik|, ties to the smallest position; rows with a nonzero entry are listed
         const int cc = cmap[k];
@@ -639,19 +965,67 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
             pv = D.W[(size_t)pr * S + cc];
             __syncthreads(); // everybody has read rowAt before the interchange
             if (tid == 0) {
-                g_swap_pos(D, k, ppos); // linalg.rs:107-114
+                g_swap_pos(g, D, k, ppos); // linalg.rs:107-114
                 D.pivr[cc] = pr;
             }
         }
         g.stat_real += 1;
+        gtick(g, GP_SEARCH);
+        gcount(g, GP_SLOW_STEPS, 1);
+        if (transposed) ++cc_next; // this core column is done
+        if (cooldown > 0) --cooldown;
         if (pv != 0.0 && n_list > 1) {
+            // compact the pivot row right of the pivot: pattern columns + values, mask words
+            __syncthreads();
+            if (tid == 0) {
+                g.sctl[5] = 0;
+                g.sctl[6] = 0;
+            }
+            __syncthreads();
+            {
+                const double *__restrict__ prow = D.W + (size_t)pr * S;
+                const unsigned *__restrict__ pmask = D.rmask + (size_t)pr * MW;
+                const int q0 = (cc + 1) >> 5;
+                bool badrow = false;
+                for (int q = q0 + tid; q < MW; q += g.NT) {
+                    unsigned word = pmask[q];
+                    if (q == q0) {
+                        const int lo = cc + 1 - 32 * q0;
+                        word = lo >= 32 ? 0u : (word & ~((1u << lo) - 1u));
+                    }
+                    if (!word) continue;
+                    const int wl = atomicAdd(&g.sctl[6], 1);
+                    D.pwq[wl] = q;
+                    D.pwb[wl] = word;
+                    int at = atomicAdd(&g.sctl[5], __popc(word));
+                    while (word) {
+                        const int b = __ffs(word) - 1;
+                        word &= word - 1;
+                        const int j = 32 * q + b;
+                        const double u = prow[j];
+                        badrow = badrow || !isfinite(u);
+                        D.pcols[at] = j;
+                        D.pvals[at] = u;
+                        ++at;
+                    }
+                }
+                if (badrow) g.sctl[1] = 1;
+            }
+            __syncthreads();
+            if (g.sctl[1]) return false;
+            const int ncols = g.sctl[5], nwords = g.sctl[6];
+            if (epoch_valid && (ncols > 0 || D.W[(size_t)pr * S + nr] != 0.0)) {
+                epoch_valid = false; // W changes: the column maxima are stale
+                if (g.sctl[8] < 2) cooldown = 4; // the window did not pay: a few plain steps first
+            }
             if (n_list <= 2 * g.NW) { // narrow step: the master's own warps, no grid barrier
-                __syncthreads();
-                update_rows(g, D, warp, g.NW, n_list, k, cc, pr, pv);
+                update_rows(g, D, warp, g.NW, n_list, cc, pr, pv, ncols, nwords);
                 __syncthreads();
             } else {
                 if (tid == 0) {
                     D.job[JI_NLIST] = n_list;
+                    D.job[JI_NCOLS] = ncols;
+                    D.job[JI_NWORDS] = nwords;
                     D.jobd[JD_0] = pv;
                 }
                 dispatch(g, D, T, Bt, J_UPDATE, k, cc, pr);
@@ -660,6 +1034,7 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
             if (D.job[JI_EXOTIC] == 1) return false;
         }
         __syncthreads();
+        gtick(g, GP_UPDATE);
         ++k;
     }
     // the row left at the last position is the pivot row of the last column
@@ -675,83 +1050,12 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
     }
     // ---- back substitution (linalg.rs:292-297) ----
     dispatch(g, D, T, Bt, J_BACK_PREP);
-    bool nonfinite = D.job[JI_EXOTIC] == 2;
-    for (int cc = nr - 1; cc >= 0; --cc) {
-        if (!D.pend[cc]) continue;
-        const int i = D.pivr[cc];
-        const double *__restrict__ row = D.W + (size_t)i * S;
-        const unsigned *__restrict__ mask = D.rmask + (size_t)i * MW;
-        double s = row[nr];
-        const double d = row[cc];
-        const int q0 = (cc + 1) >> 5;
-        // the CTA forms the products u_ij * y_j of the row's pattern in column order, up to
-        // kBufTerms words' worth at a time; warp 0's lanes then subtract them one after the
-        // other (every lane the same chain, so the result is in every lane)
-        for (int qb = q0; qb < MW; qb += g.NT) {
-            const int q = qb + tid;
-            unsigned word = (q < MW) ? mask[q] : 0u;
-            if (q == q0) {
-                const int lo = cc + 1 - 32 * q0;
-                word = lo >= 32 ? 0u : (word & ~((1u << lo) - 1u));
-            }
-            // exclusive prefix of the popcounts over the CTA
-            const int pc = __popc(word);
-            int incl = pc;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int t = __shfl_up_sync(kFull, incl, off);
-                if (lane >= off) incl += t;
-            }
-            if (lane == 31) g.scan[warp] = incl;
-            __syncthreads();
-            int base = 0, total = 0;
-            for (int w = 0; w < g.NW; ++w) {
-                const int a = g.scan[w];
-                if (w < warp) base += a;
-                total += a;
-            }
-            int at = base + incl - pc;
-            // a thread's 32 columns may straddle the buffer: rounds of kBufTerms terms
-            for (int r0 = 0; r0 < total; r0 += kBufTerms) {
-                unsigned wbits = word;
-                int pos = at;
-                while (wbits) {
-                    const int b = __ffs(wbits) - 1;
-                    wbits &= wbits - 1;
-                    if (pos >= r0 && pos < r0 + kBufTerms) {
-                        const int j = 32 * q + b;
-                        g.sbuf[pos - r0] = __dmul_rn(row[j], D.ycore[j]);
-                    }
-                    ++pos;
-                }
-                __syncthreads();
-                if (warp == 0) {
-                    const int n = min(kBufTerms, total - r0);
-                    int t = 0;
-                    for (; t + 4 <= n; t += 4) {
-                        const double p0 = g.sbuf[t], p1 = g.sbuf[t + 1], p2 = g.sbuf[t + 2], p3 = g.sbuf[t + 3];
-                        s = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(s, p0), p1), p2), p3);
-                    }
-                    for (; t < n; ++t) s = __dsub_rn(s, g.sbuf[t]);
-                    if (lane == 0) g.n_solve += 2ull * n;
-                }
-                __syncthreads();
-            }
-            __syncthreads(); // scan[] is rewritten by the next batch of words
-        }
-        if (warp == 0) {
-            const double yi = (d == 1.0) ? s : __ddiv_rn(s, d);
-            if (lane == 0) {
-                D.ycore[cc] = yi;
-                g.sctl[3] = isfinite(yi) ? 0 : 1;
-                g.n_solve += 1;
-            }
-        }
-        __syncthreads();
-        nonfinite = nonfinite || g.sctl[3] != 0;
-        __syncthreads();
-    }
+    gtick(g, GP_BACK_PREP);
+    if (tid == 0) D.job[JI_CURSOR] = 0;
+    dispatch(g, D, T, Bt, J_BACKSUB);
+    const bool nonfinite = D.job[JI_EXOTIC] == 2;
     dispatch(g, D, T, Bt, J_YSCATTER, transposed ? 1 : 0);
+    gtick(g, GP_BACK_CHAIN);
     if (nonfinite) {
         // see dz_core.cu: the literal arithmetic multiplies a non-finite component into every
         // earlier row, by an exact zero wherever the row has no entry in that column
@@ -820,11 +1124,16 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
     {
         double *dp = reinterpret_cast<double *>(smem_raw);
         g.sbuf = dp, dp += kBufTerms;
+        g.wmax = reinterpret_cast<unsigned long long *>(dp), dp += kWin;
         g.red_key = dp, dp += 2 * 4 * kMaxWarps;
         int *ip = reinterpret_cast<int *>(dp);
         g.red_idx = ip, ip += 2 * 4 * kMaxWarps;
-        g.scan = ip, ip += 2 * kMaxWarps;
+        g.scan = ip, ip += 4 * kMaxWarps;
         g.sctl = ip, ip += 16;
+        g.heap = ip, ip += kHeapCap;
+        g.wcnt = ip, ip += kWin;
+        g.wcand = ip, ip += 4 * kWin;
+        g.prof = (Bt.prof && g.blk == 0) ? reinterpret_cast<long long *>(ip) : nullptr;
     }
     const int M = g.M, Nn = g.Nn, tid = g.tid;
 
@@ -848,6 +1157,11 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
             long long pivots = 0, n_primal = 0;
             unsigned long long hash = 0xcbf29ce484222325ULL, n_upd = 0;
             bool handed_over = false;
+            if (g.prof) {
+                if (tid < 16) g.prof[tid] = 0;
+                __syncthreads();
+                g.t_last = clock64();
+            }
             long long dirty = 0; // doubles of W any solve of this LP has used
             g.stat_core = g.stat_real = g.stat_grid = 0;
             while (true) {
@@ -865,6 +1179,7 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
                         if (r != r) p0 = f3;
                     }
                 }
+                gtick(g, GP_STATUS);
                 bool primal_step;
                 double mu;
                 if (q0 >= 0 && p0 >= 0) {
@@ -895,15 +1210,17 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
                 // ---- the coupled core of this basis ----
                 dispatch(g, D, T, Bt, J_LISTS_COUNT);
                 {
-                    int nrow = 0, ncol = 0;
+                    int run[4] = {0, 0, 0, 0};
                     for (int b = 0; b < g.nblocks; ++b) { // every master thread the same short scan
-                        if (tid == 0) {
-                            D.bcnt[2 * g.nblocks + b] = nrow;
-                            D.bcnt[3 * g.nblocks + b] = ncol;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (tid == 0) D.bcnt[(4 + q) * g.nblocks + b] = run[q];
+                            run[q] += D.bcnt[q * g.nblocks + b];
                         }
-                        nrow += D.bcnt[b];
-                        ncol += D.bcnt[g.nblocks + b];
                     }
+                    const int nrow = run[0], ncol = run[1];
+                    g.nse[0] = run[2];
+                    g.nse[1] = run[3];
                     if (nrow != ncol) {
                         handed_over = true;
                         break;
@@ -919,6 +1236,7 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
                     g.stat_core += 2 * (unsigned long long)nrow * (unsigned long long)g.S; // two solves
                 }
                 dispatch(g, D, T, Bt, J_LISTS_WRITE);
+                gtick(g, GP_LISTS);
                 int p = p0, q = q0;
                 bool failed = false;
                 for (int pass = 0; pass < 2; ++pass) {
@@ -927,11 +1245,15 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
                         handed_over = true;
                         break;
                     }
-                    if (transposed) dispatch(g, D, T, Bt, J_PRICE);
+                    if (transposed) {
+                        dispatch(g, D, T, Bt, J_PRICE);
+                        gtick(g, GP_PRICE);
+                    }
                     if (pass == 0) {
                         if (tid == 0) D.jobd[JD_0] = mu;
                         dispatch(g, D, T, Bt, J_RATIO, primal_step ? 1 : 0);
                         const int r = reduce_partials(g, D, 0, nullptr);
+                        gtick(g, GP_RATIO);
                         if (primal_step) {
                             p = r;
                             if (p < 0) {
@@ -998,6 +1320,11 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
                 ++pivots;
                 if (primal_step) ++n_primal;
                 __syncthreads();
+                gtick(g, GP_VECUPD);
+            }
+            if (g.prof) {
+                __syncthreads();
+                if (tid < 16) Bt.prof[(size_t)lp * 16 + tid] = g.prof[tid];
             }
             // leave the working matrix all-zero: the general kernel's interval mode, which
             // takes over a handed-over LP in the same workspace, expects that
@@ -1103,9 +1430,20 @@ size_t grid_workspace(int M, int Nn, long long nnz, int nblocks, long long w_cap
     g.pivr = (int *)take(4 * Ms);
     g.pend = (int *)take(4 * Ms);
     g.list = (int *)take(4 * (Ms + 32));
+    g.pcols = (int *)take(4 * (Ms + 32));
+    g.pwq = (int *)take(4 * (Ms / 32 + 32));
+    g.pwb = (unsigned *)take(4 * (Ms / 32 + 32));
+    g.pvals = (double *)take(8 * (Ms + 32));
+    g.colmax = (unsigned long long *)take(8 * Ms);
+    g.colcnt = (int *)take(4 * Ms);
+    g.colcand = (int *)take(4 * 4 * Ms);
+    g.rlast = (int *)take(4 * Ms);
+    g.done = (int *)take(4 * Ms);
     g.where = (int *)take(4 * (Ms + Ns));
     g.pidx = (int *)take(4 * 4 * (size_t)nblocks);
-    g.bcnt = (int *)take(4 * 4 * (size_t)nblocks);
+    g.bcnt = (int *)take(4 * 8 * (size_t)nblocks);
+    g.seu = (int *)take(4 * Ms);
+    g.set_ = (int *)take(4 * Ms);
     g.job = (int *)take(4 * JI_WORDS);
     g.bar = (unsigned *)take(4 * 4);
     g.rmask = (unsigned *)take(4 * Ms * (size_t)((M + 31) / 32));
@@ -1115,7 +1453,9 @@ size_t grid_workspace(int M, int Nn, long long nnz, int nblocks, long long w_cap
     return off;
 }
 
-size_t grid_smem_bytes() { return (size_t)kBufTerms * 8 + 2 * 4 * kMaxWarps * 8 + (2 * 4 * kMaxWarps + 2 * kMaxWarps + 16) * 4 + 16; }
+size_t grid_smem_bytes() {
+    return (size_t)kBufTerms * 8 + kWin * 8 + 2 * 4 * kMaxWarps * 8 + (2 * 4 * kMaxWarps + 4 * kMaxWarps + 16 + 5 * kWin + kHeapCap) * 4 + 16 * 8 + 16;
+}
 
 int launch_grid(const TemplateDev &T, const BatchDev &Bt, const GridDev &D, const LaunchPlan &plan, void *stream,
                 std::string *err) {

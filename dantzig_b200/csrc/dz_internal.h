@@ -93,8 +93,16 @@ struct GridDev {
     double *W;     // working core, dense rows of (nr + 1) | 1 doubles
     int *bas, *nb, *rowAt, *posOf, *rowcnt, *srow, *spos, *rmapR, *rlist, *pmap, *plist, *pivr, *pend;
     int *list;     // rows with a nonzero in the current pivot column
+    int *pcols, *pwq; // compacted pivot row: pattern columns; mask word indices
+    unsigned *pwb;    // ... and the mask words
+    double *pvals;    // ... and the values
+    unsigned long long *colmax; // epoch: max |a_ij| of each remaining core column, as a bit pattern
+    int *colcnt, *colcand;      // ... how many rows attain it, and up to four of them
+    int *rlast;                 // last column of each core row's nonzero pattern
+    int *done;                  // back-substitution: component of this core column is final
     int *where;    // column -> nonbasic slot k >= 0, or -1 - (basis position)
     int *pidx, *bcnt, *job;
+    int *seu, *set_; // positions (columns of B / of B^T) whose elimination step is not a no-op from the start
     unsigned *bar;   // grid barrier: arrivals, generation
     unsigned *rmask; // [nr][ceil(nr/32)] columns of each core row that may be nonzero
     long long w_cap; // doubles available at W

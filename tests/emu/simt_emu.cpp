@@ -127,6 +127,7 @@ bool step_block(Block &b) {
     const size_t n = b.th.size();
     bool progressed = false;
     for (Thread &t : b.th) {
+        if (!t.done && t.wait == OP_YIELD) t.wait = OP_NONE; // a polling thread gets another turn
         if (t.done || t.wait != OP_NONE) continue;
         g_cur = &t;
         emu_switch(&g_sched_sp, t.sp);
@@ -156,7 +157,7 @@ bool step_block(Block &b) {
             if (!any) op = t.wait, any = true;
             else if (t.wait != op) uniform = false;
         }
-        if (!any || op == OP_NONE || op == OP_SYNCTHREADS || op == OP_GRIDSYNC) continue;
+        if (!any || op == OP_NONE || op == OP_SYNCTHREADS || op == OP_GRIDSYNC || op == OP_YIELD) continue;
         if (!uniform) {
             std::fprintf(stderr, "simt_emu: block %u warp %zu diverged across different collectives\n",
                          b.bid.x, w0 / 32);

@@ -45,7 +45,7 @@
 
 namespace emu {
 
-enum Op { OP_NONE = 0, OP_BALLOT, OP_SHFL, OP_RMAX_U, OP_RMIN_U, OP_RMAX_I, OP_RMIN_I, OP_SYNCWARP, OP_SYNCTHREADS, OP_GRIDSYNC };
+enum Op { OP_NONE = 0, OP_BALLOT, OP_SHFL, OP_RMAX_U, OP_RMIN_U, OP_RMAX_I, OP_RMIN_I, OP_SYNCWARP, OP_SYNCTHREADS, OP_GRIDSYNC, OP_YIELD };
 
 struct Dim3 {
     unsigned x = 1, y = 1, z = 1;
@@ -134,6 +134,8 @@ int launch_coop(Kern kern, int grid, int block, size_t smem_bytes, Args... args)
 
 inline unsigned char *dyn_smem() { return g_blk->smem; }
 inline void grid_sync() { collective(OP_GRIDSYNC, 0, 0); }
+// spin-wait loops on flags other threads set must give the other fibers a turn
+inline void yield() { collective(OP_YIELD, 0, 0); }
 
 } // namespace emu
 
@@ -214,6 +216,12 @@ inline unsigned atomicOr(unsigned *p, unsigned v) {
     return old;
 }
 inline double __longlong_as_double(long long v) { return emu_unbits<double>((uint64_t)v); }
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) {
+    const unsigned long long old = *p;
+    *p = std::max(old, v);
+    return old;
+}
+inline long long __double_as_longlong(double v) { return (long long)emu_bits(v); }
 inline unsigned atomicExch(unsigned *p, unsigned v) {
     const unsigned old = *p;
     *p = v;

@@ -121,7 +121,8 @@ def test_random_ragged_models_on_device(oracle):
     assert seen[0] > 20 and seen[1] > 5 and seen[2] > 5      # the fuzz reaches all outcomes
 
 
-@pytest.mark.parametrize("shape", [(-1, 0), (2, 1), (2, 2)], ids=["warp", "cta-smem", "cta-hbm"])
+@pytest.mark.parametrize("shape", [(-1, 0), (2, 1), (2, 2), (0, 4), (2, 5, 3)],
+                         ids=["warp", "cta-smem", "cta-hbm", "core-on-chip", "grid-3ctas"])
 def test_integer_data_batches(oracle, shape):
     """Degenerate batches: small-integer coefficients make ties in every pivot
     search and ratio test, exact zeros in the data, infeasible and unbounded LPs."""
@@ -139,7 +140,8 @@ def test_integer_data_batches(oracle, shape):
     st = dense_structure(m, n, senses, has_lb, has_ub)
     th = dense_theta(A, b, c, senses, lb, ub, has_lb, has_ub, minimize=True)
     t = Template(st)
-    res = solve_batch(t, th, trace_cap=64, worker_warps=shape[0], basis_home=shape[1], max_pivots=500)
+    res = solve_batch(t, th, trace_cap=64, worker_warps=shape[0], basis_home=shape[1], max_pivots=500,
+                      ctas_per_sm=shape[2] if len(shape) > 2 else 0)
     hist = np.zeros(5, int)
     for i in range(B):
         o = oracle.lower(model_from_theta(st, th[i])).solve(oracle.LITERAL, max_pivots=500, trace_cap=64)
