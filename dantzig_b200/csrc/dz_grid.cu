@@ -45,7 +45,14 @@ constexpr int kBufTerms = 2048; // ordered products of one back-substitution row
 #define DZ_GRID_HEAP_CAP 4096 // tests shrink it to exercise the overflow path
 #endif
 constexpr int kHeapCap = DZ_GRID_HEAP_CAP; // positions disturbed by interchanges, waiting for their step (master, shared memory)
-constexpr int kWin = 64;      // core columns per look-ahead window of the transposed elimination
+#ifndef DZ_GRID_TILE
+#define DZ_GRID_TILE 256
+#endif
+#ifndef DZ_GRID_WIN
+#define DZ_GRID_WIN 64
+#endif
+constexpr int kTile = DZ_GRID_TILE; // pattern columns per work item of an elimination update (multiple of 32)
+constexpr int kWin = DZ_GRID_WIN;      // core columns per look-ahead window of the transposed elimination
 constexpr int kWarpBuf = kBufTerms / 16; // ... per warp in the grid-wide back-substitution (16 warps per CTA)
 
 // Slots of the optional cycle profile of the master CTA (BatchDev::prof, 16 per LP).
@@ -127,27 +134,35 @@ __device__ __forceinline__ void update_rows(G &g, const GridDev &D, int first, i
     const long long S = g.S;
     const double urhs = D.W[(size_t)pr * S + nr];
     bool bad = !isfinite(urhs);
-    for (int e = first; e < n_list; e += stride) {
+    // work items are (candidate row, tile of kTile pattern columns); tile 0 also carries the
+    // right-hand side and the row's pattern bookkeeping
+    const int ntile = max(1, (ncols + kTile - 1) / kTile);
+    const long long items = (long long)n_list * ntile;
+    for (long long it = first; it < items; it += stride) {
+        const int e = (int)(it / ntile), tile = (int)(it - (long long)e * ntile);
         const int i = D.list[e];
         if (i == pr) continue;
         double *__restrict__ row = D.W + (size_t)i * S;
-        unsigned *__restrict__ imask = D.rmask + (size_t)i * MW;
         const double l = fast_div(row[cc], pv);
         bad = bad || !isfinite(l);
+        const int t0 = tile * kTile, t1 = min(ncols, t0 + kTile);
 #pragma unroll 4
-        for (int t = lane; t < ncols; t += 32) {
+        for (int t = t0 + lane; t < t1; t += 32) {
             const int j = D.pcols[t];
             row[j] = __dsub_rn(row[j], __dmul_rn(l, D.pvals[t]));
         }
-        for (int t = lane; t < nwords; t += 32) imask[D.pwq[t]] |= D.pwb[t]; // fill pattern
-        if (lane == 0) {
-            if (ncols > 0) D.rlast[i] = max(D.rlast[i], D.rlast[pr]);
-            unsigned long long cnt = 2ull * ncols + 1;
-            if (urhs != 0.0) {
-                row[nr] = __dsub_rn(row[nr], __dmul_rn(l, urhs));
-                cnt += 2;
+        if (tile == 0) {
+            unsigned *__restrict__ imask = D.rmask + (size_t)i * MW;
+            for (int t = lane; t < nwords; t += 32) imask[D.pwq[t]] |= D.pwb[t]; // fill pattern
+            if (lane == 0) {
+                if (ncols > 0) D.rlast[i] = max(D.rlast[i], D.rlast[pr]);
+                unsigned long long cnt = 2ull * ncols + 1;
+                if (urhs != 0.0) {
+                    row[nr] = __dsub_rn(row[nr], __dmul_rn(l, urhs));
+                    cnt += 2;
+                }
+                g.n_lu += cnt;
             }
-            g.n_lu += cnt;
         }
     }
     if (__ballot_sync(kFull, bad) && lane == 0) D.job[JI_EXOTIC] = 1;
@@ -492,39 +507,57 @@ __device__ __forceinline__ void exec_job(G &g, const GridDev &D, const TemplateD
                 }
                 unsigned nzw = __ballot_sync(kFull, word != 0u);
                 while (nzw) {
-                    const int wq = __ffs(nzw) - 1;
-                    nzw &= nzw - 1;
-                    const unsigned bits = __shfl_sync(kFull, word, wq);
-                    const bool has = (bits >> lane) & 1u;
-                    const int j = 32 * (wb + wq) + lane;
-                    for (;;) { // wait for the components this group of columns needs
-                        const bool ok = !has || *((volatile int *)&D.done[j]) != 0;
+                    // four mask words (128 columns) per trip: their flags, then their loads, are
+                    // all in flight together
+                    bool has[4];
+                    int jc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        has[u] = false;
+                        jc[u] = 0;
+                        if (nzw) {
+                            const int wq = __ffs(nzw) - 1;
+                            nzw &= nzw - 1;
+                            const unsigned bits = __shfl_sync(kFull, word, wq);
+                            has[u] = (bits >> lane) & 1u;
+                            jc[u] = 32 * (wb + wq) + lane;
+                        }
+                    }
+                    for (;;) { // wait for the components these columns need
+                        bool ok = true;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) ok = ok && (!has[u] || *((volatile int *)&D.done[jc[u]]) != 0);
                         if (__ballot_sync(kFull, !ok) == 0u) break;
 #ifdef DZ_EMU
                         emu::yield();
 #endif
                     }
                     __threadfence();
-                    double p = 0.0;
-                    if (has) {
+                    double uu[4], yy[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uu[u] = has[u] ? row[jc[u]] : 0.0;
 #ifdef DZ_EMU
-                        const double yj = D.ycore[j];
+                        yy[u] = has[u] ? D.ycore[jc[u]] : 0.0;
 #else
-                        const double yj = __ldcg(&D.ycore[j]);
+                        yy[u] = has[u] ? __ldcg(&D.ycore[jc[u]]) : 0.0;
 #endif
-                        p = __dmul_rn(row[j], yj);
                     }
-                    const bool take = has && p != 0.0; // subtracting an exact zero changes nothing
-                    const unsigned mk = __ballot_sync(kFull, take);
-                    if (nbuf + __popc(mk) > kWarpBuf) { // flush the staged products, in order
-                        __syncwarp();
-                        for (int t = 0; t < nbuf; ++t) s = __dsub_rn(s, buf[t]);
-                        ops += 2ull * nbuf;
-                        nbuf = 0;
-                        __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double p = __dmul_rn(uu[u], yy[u]);
+                        const bool take = has[u] && p != 0.0; // subtracting an exact zero changes nothing
+                        const unsigned mk = __ballot_sync(kFull, take);
+                        if (nbuf + __popc(mk) > kWarpBuf) { // flush the staged products, in order
+                            __syncwarp();
+                            for (int t = 0; t < nbuf; ++t) s = __dsub_rn(s, buf[t]);
+                            ops += 2ull * nbuf;
+                            nbuf = 0;
+                            __syncwarp();
+                        }
+                        if (take) buf[nbuf + __popc(mk & lt)] = p;
+                        nbuf += __popc(mk);
                     }
-                    if (take) buf[nbuf + __popc(mk & lt)] = p;
-                    nbuf += __popc(mk);
                 }
             }
             __syncwarp();
@@ -775,29 +808,48 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
             }
             if (tid == 0) g.sctl[8] = 0; // fast commits of this window
             __syncthreads();
-            const int qa = epoch_lo >> 5, qb = (epoch_hi - 1) >> 5;
+            const int qa = epoch_lo >> 5, qb = (epoch_hi - 1) >> 5; // at most three mask words
             bool wbad = false;
+            const int nwq = qb - qa + 1;
             for (int pass = 0; pass < 2; ++pass) {
-                for (int i = tid; i < nr; i += g.NT) {
+                // work items are (row, mask word of the window): a dense row's words go to
+                // neighbouring threads instead of all to one
+                for (int it = tid; it < nr * nwq; it += g.NT) {
+                    const int i = it / nwq, q = qa + (it - i * nwq);
+                    unsigned word = D.rmask[(size_t)i * MW + q];
+                    const int lo = epoch_lo - 32 * q, hi = epoch_hi - 32 * q; // keep bits [lo, hi)
+                    if (lo > 0) word = lo >= 32 ? 0u : (word & ~((1u << lo) - 1u));
+                    if (hi < 32) word = hi <= 0 ? 0u : (word & ((1u << hi) - 1u));
+                    if (!word) continue; // nothing of this row in this part of the window
                     if (D.posOf[rlist[i]] < k) continue;
                     const double *__restrict__ row = D.W + (size_t)i * S;
-                    const unsigned *__restrict__ mask = D.rmask + (size_t)i * MW;
-                    for (int q = qa; q <= qb; ++q) {
-                        unsigned word = mask[q];
-                        while (word) {
-                            const int bbit = __ffs(word) - 1;
-                            word &= word - 1;
-                            const int j = 32 * q + bbit;
-                            if (j < epoch_lo || j >= epoch_hi) continue;
-                            const double v = row[j];
+                    while (word) { // eight independent loads at a time
+                        int jj[8];
+                        double vv8[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            jj[e] = -1;
+                            if (word) {
+                                jj[e] = 32 * q + __ffs(word) - 1;
+                                word &= word - 1;
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) vv8[e] = jj[e] >= 0 ? row[jj[e]] : 0.0;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (jj[e] < 0) continue;
+                            const double v = vv8[e];
                             wbad = wbad || !isfinite(v);
                             if (v == 0.0) continue;
                             const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(v));
+                            const int slot_j = jj[e] - epoch_lo;
                             if (pass == 0) {
-                                atomicMax(&g.wmax[j - epoch_lo], key);
-                            } else if (key == g.wmax[j - epoch_lo]) {
-                                const int slot = atomicAdd(&g.wcnt[j - epoch_lo], 1);
-                                if (slot < 4) g.wcand[4 * (j - epoch_lo) + slot] = i;
+                                // most entries are not the maximum: look before the atomic
+                                if (key > *((volatile unsigned long long *)&g.wmax[slot_j])) atomicMax(&g.wmax[slot_j], key);
+                            } else if (key == g.wmax[slot_j]) {
+                                const int slot = atomicAdd(&g.wcnt[slot_j], 1);
+                                if (slot < 4) g.wcand[4 * slot_j + slot] = i;
                             }
                         }
                     }
@@ -933,6 +985,8 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
         cd.idx[0] = -1; // idx = position (unique per row)
         bool bad = false;
         for (int i = tid; i < nr; i += g.NT) {
+            // only rows whose pattern has this column can hold a nonzero there
+            if (!((D.rmask[(size_t)i * MW + (cc >> 5)] >> (cc & 31)) & 1u)) continue;
             const int pos = D.posOf[rlist[i]];
             if (pos >= k) {
                 const double v = D.W[(size_t)i * S + cc];
@@ -1018,7 +1072,7 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
                 epoch_valid = false; // W changes: the column maxima are stale
                 if (g.sctl[8] < 2) cooldown = 4; // the window did not pay: a few plain steps first
             }
-            if (n_list <= 2 * g.NW) { // narrow step: the master's own warps, no grid barrier
+            if ((long long)n_list * max(ncols, 32) <= 64 * g.NW) { // small step: the master's own warps, no grid barrier
                 update_rows(g, D, warp, g.NW, n_list, cc, pr, pv, ncols, nwords);
                 __syncthreads();
             } else {
