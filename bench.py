@@ -11,8 +11,8 @@ Workloads
   c5 (default)  BASELINE configs[4]: LPs of m=64 x n=128 (lowered 192x448), the batch the
                 multi-GPU metric is quoted on.  A FIXED total batch (--total-lps) is sharded
                 by contiguous LP id over the N ranks: STRONG scaling.  The full 262 144-LP
-                batch is hours of GPU time; the default total is sized for a step of a few
-                seconds on one GPU.
+                batch is hours of GPU time; the default total (9472 = 8 x 1184) keeps a step
+                at ~25 s on one GPU, so the driver's 25-step run fits its per-N time limit.
   c2            BASELINE configs[1]: 4096 LPs of m=32 x n=64 (lowered 96x224) on one GPU; with
                 N > 1 every rank gets its own 4096 (weak scaling, as in round 1).
   c3, c4        BASELINE configs[2], configs[3]: ONE large LP (dense 2000x4000 packing LP;
@@ -51,7 +51,7 @@ import numpy as np  # noqa: E402
 
 BATCHED = {
     # name: (m, n, generator name, default total LPs, LPs per core per CPU step, oracle parity sample)
-    "c5": (64, 128, "config5", 2368, 1, 3),
+    "c5": (64, 128, "config5", 9472, 1, 3),
     "c2": (32, 64, "config2", 4096, 2, 8),
 }
 SINGLE = {"c3": "dense packing LP m=2000 x n=4000 (lowered 6000x14000)",

@@ -49,7 +49,8 @@ namespace dz {
 
 namespace {
 
-enum { CC_K = 0, CC_C, CC_PR, CC_DONE, CC_EXOTIC, CC_LP, CC_FLAG, CC_TOTAL, CC_NR, CC_WORDS = 16 };
+enum { CC_K = 0, CC_C, CC_PR, CC_DONE, CC_EXOTIC, CC_LP, CC_FLAG, CC_TOTAL, CC_NR, CC_CURSOR, CC_WORDS = 16 };
+constexpr int kCoreWarpBuf = 64; // staged products per warp in the back-substitution
 
 // Slots of the optional per-LP cycle profile (BatchDev::prof, 16 per LP).
 enum { CP_STATUS = 0, CP_LISTS, CP_GATHER, CP_ELIM, CP_BACK, CP_PRICE, CP_RATIO, CP_UPDATE, CP_REAL_STEPS,
@@ -62,7 +63,7 @@ struct Core {
     // per-LP state, shared memory
     double *x, *xb, *dxv, *vv, *z, *zb, *dzv;
     double *ycore; // [M] solution of the core system by core column
-    double *pbuf;  // [M] ordered nonzero products of one back-substitution row
+    double *pbuf;  // [16 * kCoreWarpBuf (>= M)] per-warp staging of a back-substitution row's ordered products
     double *pvs;   // [2] pivot value of the current step
     int *bas, *nb;
     int *rowAt, *posOf;   // [M] interchanges of the running elimination (rows of B or of B^T)
@@ -73,6 +74,7 @@ struct Core {
     int *pmap, *plist;    // basis position -> core index / back
     int *cstart;          // [M+1] first flat CSC entry of each core position (scatter)
     int *pivr;            // [M] core column -> core row that is its pivot row
+    int *done;            // [M] back-substitution: this core column's component is final
     unsigned *rmask;      // [M][NQ] columns of each core row that may be nonzero
     int *scan;            // [2 * kMaxWarps]
     int *ctl;             // [CC_WORDS]
@@ -271,6 +273,7 @@ __device__ __forceinline__ bool core_solve(Core &c, const TemplateDev &T, const 
             c.rowAt[i] = i;
             c.posOf[i] = i;
             c.pivr[i] = -1;
+            c.done[i] = 0;
             y[i] = 0.0;
         }
         if (tid < CC_WORDS && tid != CC_LP) c.ctl[tid] = 0;
@@ -552,11 +555,21 @@ __device__ __forceinline__ bool core_solve(Core &c, const TemplateDev &T, const 
     ctick(c, CP_ELIM);
 
     // ---- back substitution (linalg.rs:292-297), core columns nr-1 .. 0 -----------------------
-    if (warp == 0) {
+    // LEVEL-SCHEDULED by data flow: every warp takes core columns in descending order from a
+    // shared cursor and waits, 32 pattern columns at a time, for the components its row needs
+    // (done[j] in shared memory); rows that do not depend on each other proceed side by side.
+    // A row's products u_ij * y_j are formed by the lanes, staged in column order in the
+    // warp's slice of pbuf and subtracted one after the other (ascending j, linalg.rs:294).
+    {
         const unsigned lt = (1u << lane) - 1u;
+        double *buf = c.pbuf + warp * kCoreWarpBuf;
         unsigned long long ops = 0;
-        int nonfinite = 0;
-        for (int cc = nr - 1; cc >= 0; --cc) {
+        for (;;) {
+            int idx = 0;
+            if (lane == 0) idx = atomicAdd(&c.ctl[CC_CURSOR], 1);
+            idx = __shfl_sync(kFull, idx, 0);
+            if (idx >= nr) break;
+            const int cc = nr - 1 - idx;
             const int i = c.pivr[cc];
             const double *__restrict__ row = wrow(c, i);
             double s = row[nr];
@@ -571,33 +584,49 @@ __device__ __forceinline__ bool core_solve(Core &c, const TemplateDev &T, const 
                 bits = lo <= 0 ? bits : (lo >= 32 ? 0u : (bits & ~((1u << lo) - 1u)));
                 if (!bits) continue; // warp-uniform
                 const int j = 32 * q + lane;
+                const bool has = (bits >> lane) & 1u;
+                for (;;) { // wait for the components these columns need
+                    const bool ok = !has || *((volatile int *)&c.done[j]) != 0;
+                    if (__ballot_sync(kFull, !ok) == 0u) break;
+#ifdef DZ_EMU
+                    emu::yield();
+#endif
+                }
                 double uu = 0.0, yj = 0.0;
-                if ((bits >> lane) & 1u) {
+                if (has) {
                     uu = row[j];
-                    yj = c.ycore[j];
+                    yj = *((volatile double *)&c.ycore[j]);
                 }
                 const bool take = uu != 0.0 && yj != 0.0;
                 const unsigned mk = __ballot_sync(kFull, take);
-                if (take) c.pbuf[cnt + __popc(mk & lt)] = __dmul_rn(uu, yj);
+                if (cnt + __popc(mk) > kCoreWarpBuf) { // flush the staged products, in order
+                    __syncwarp();
+                    for (int t = 0; t < cnt; ++t) s = __dsub_rn(s, buf[t]);
+                    ops += 2ull * cnt;
+                    cnt = 0;
+                    __syncwarp();
+                }
+                if (take) buf[cnt + __popc(mk & lt)] = __dmul_rn(uu, yj);
                 cnt += __popc(mk);
             }
             __syncwarp();
             int t = 0;
             for (; t + 4 <= cnt; t += 4) { // ascending column order (linalg.rs:294)
-                const double p0 = c.pbuf[t], p1 = c.pbuf[t + 1], p2 = c.pbuf[t + 2], p3 = c.pbuf[t + 3];
+                const double p0 = buf[t], p1 = buf[t + 1], p2 = buf[t + 2], p3 = buf[t + 3];
                 s = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(s, p0), p1), p2), p3);
             }
-            for (; t < cnt; ++t) s = __dsub_rn(s, c.pbuf[t]);
+            for (; t < cnt; ++t) s = __dsub_rn(s, buf[t]);
             const double yi = (d == 1.0) ? s : __ddiv_rn(s, d);
-            if (lane == 0) c.ycore[cc] = yi;
-            nonfinite |= !isfinite(yi);
+            if (lane == 0) {
+                c.ycore[cc] = yi;
+                __threadfence_block();
+                *((volatile int *)&c.done[cc]) = 1;
+                if (!isfinite(yi)) c.ctl[CC_FLAG] = 1;
+            }
             ops += 2ull * cnt + 1ull;
             __syncwarp();
         }
-        if (lane == 0) {
-            c.n_solve += ops;
-            if (nonfinite) c.ctl[CC_FLAG] = 1;
-        }
+        if (lane == 0) c.n_solve += ops;
     }
     __syncthreads();
     for (int cc = tid; cc < nr; cc += c.NT) y[clist[cc]] = c.ycore[cc];
@@ -672,7 +701,7 @@ __device__ __forceinline__ void core_hand_over(Core &c, const BatchDev &Bt, long
 }
 
 template <int NQ>
-__global__ void __launch_bounds__(NQ <= 4 ? 128 : 256, NQ <= 4 ? 3 : 1)
+__global__ void __launch_bounds__(NQ <= 4 ? 128 : 512, NQ <= 4 ? 3 : 1)
 dz_core_kernel(const TemplateDev T, const BatchDev Bt, const int capW) {
 #ifdef DZ_EMU
     unsigned char *smem_raw = emu::dyn_smem();
@@ -698,7 +727,7 @@ dz_core_kernel(const TemplateDev T, const BatchDev Bt, const int capW) {
         c.dxv = dp, dp += M;
         c.vv = dp, dp += M;
         c.ycore = dp, dp += M;
-        c.pbuf = dp, dp += M;
+        c.pbuf = dp, dp += (16 * kCoreWarpBuf > M ? 16 * kCoreWarpBuf : M);
         c.z = dp, dp += Nn;
         c.zb = dp, dp += Nn;
         c.dzv = dp, dp += Nn;
@@ -721,6 +750,7 @@ dz_core_kernel(const TemplateDev T, const BatchDev Bt, const int capW) {
         c.pmap = ip, ip += M;
         c.plist = ip, ip += M;
         c.pivr = ip, ip += M;
+        c.done = ip, ip += M;
         c.cstart = ip, ip += M + 1;
         c.nb = ip, ip += Nn;
         c.rmask = reinterpret_cast<unsigned *>(ip), ip += M * NQ;
@@ -990,8 +1020,8 @@ dz_core_kernel(const TemplateDev T, const BatchDev Bt, const int capW) {
 } // namespace
 
 size_t core_fixed_smem_bytes(int M, int Nn, int NQ) {
-    const size_t doubles = 6 * (size_t)M + 3 * (size_t)Nn + 2 + 16 + 2 * 4 * kMaxWarps;
-    const size_t ints = 2 * 4 * kMaxWarps + 2 * kMaxWarps + CC_WORDS + 12 * (size_t)M + 1 + (size_t)Nn +
+    const size_t doubles = 5 * (size_t)M + std::max<size_t>(16 * kCoreWarpBuf, (size_t)M) + 3 * (size_t)Nn + 2 + 16 + 2 * 4 * kMaxWarps;
+    const size_t ints = 2 * 4 * kMaxWarps + 2 * kMaxWarps + CC_WORDS + 13 * (size_t)M + 1 + (size_t)Nn +
                         (size_t)M * NQ;
     return doubles * 8 + ints * 4 + 16;
 }

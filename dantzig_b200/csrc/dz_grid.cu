@@ -35,7 +35,7 @@ namespace {
 
 enum {
     J_EXIT = 0, J_INIT, J_INIT2, J_STATUS, J_LISTS_COUNT, J_LISTS_WRITE, J_ZERO, J_SCATTER, J_UPDATE,
-    J_BACK_PREP, J_YSCATTER, J_PRICE, J_RATIO, J_VECUPD, J_OBJ, J_EPOCH_A, J_EPOCH_B, J_BACKSUB
+    J_BACK_PREP, J_YSCATTER, J_PRICE, J_RATIO, J_VECUPD, J_OBJ, J_BACKSUB
 };
 // job descriptor words (ints) and doubles
 enum { JI_TYPE = 0, JI_A0, JI_A1, JI_A2, JI_A3, JI_A4, JI_NR, JI_EXOTIC, JI_NLIST, JI_NCOLS, JI_NWORDS, JI_CURSOR, JI_WORDS = 16 };
@@ -392,52 +392,6 @@ __device__ __forceinline__ void exec_job(G &g, const GridDev &D, const TemplateD
     case J_UPDATE:
         update_rows(g, D, g.gwarp, g.GW, D.job[JI_NLIST], a1, a2, D.jobd[JD_0], D.job[JI_NCOLS], D.job[JI_NWORDS]);
         break;
-    case J_EPOCH_A:
-    case J_EPOCH_B: {
-        // Column maxima of the remaining core columns [a0, nr) over the rows at positions >= a1,
-        // for the run of steps that follows without any change to W (see grid_solve):
-        // A: colmax[j] = max |a_ij| as a bit pattern; B: up to four rows that attain it.
-        const int nr = g.nr, MW = g.MW, from = a0, kmin = a1;
-        const long long S = g.S;
-        const int *rl = D.job[JI_A2] ? D.plist : D.rlist;
-        bool bad = false;
-        for (int i = g.gwarp; i < nr; i += g.GW) {
-            if (D.posOf[rl[i]] < kmin) continue;
-            const double *__restrict__ row = D.W + (size_t)i * S;
-            const unsigned *__restrict__ mask = D.rmask + (size_t)i * MW;
-            const int q0 = from >> 5;
-            for (int wb = q0; wb < MW; wb += 32) {
-                const int q = wb + g.lane;
-                unsigned word = (q < MW) ? mask[q] : 0u;
-                if (q == q0) {
-                    const int lo = from - 32 * q0;
-                    word = word & ~((1u << lo) - 1u);
-                }
-                unsigned nzw = __ballot_sync(kFull, word != 0u);
-                while (nzw) {
-                    const int wq = __ffs(nzw) - 1;
-                    nzw &= nzw - 1;
-                    const unsigned bits = __shfl_sync(kFull, word, wq);
-                    if ((bits >> g.lane) & 1u) {
-                        const int j = 32 * (wb + wq) + g.lane;
-                        const double v = row[j];
-                        bad = bad || !isfinite(v);
-                        const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(v));
-                        if (v != 0.0) {
-                            if (type == J_EPOCH_A) {
-                                atomicMax(&D.colmax[j], key);
-                            } else if (key == D.colmax[j]) {
-                                const int slot = atomicAdd(&D.colcnt[j], 1);
-                                if (slot < 4) D.colcand[4 * j + slot] = i;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        if (__ballot_sync(kFull, bad) && g.lane == 0) D.job[JI_EXOTIC] = 1;
-        break;
-    }
     case J_BACK_PREP: {
         // rows whose strict upper part is empty are solved at once (x/1 == x); the others are
         // left to the master's ordered chains.  pend[cc] = 1 marks them.
@@ -1488,9 +1442,6 @@ size_t grid_workspace(int M, int Nn, long long nnz, int nblocks, long long w_cap
     g.pwq = (int *)take(4 * (Ms / 32 + 32));
     g.pwb = (unsigned *)take(4 * (Ms / 32 + 32));
     g.pvals = (double *)take(8 * (Ms + 32));
-    g.colmax = (unsigned long long *)take(8 * Ms);
-    g.colcnt = (int *)take(4 * Ms);
-    g.colcand = (int *)take(4 * 4 * Ms);
     g.rlast = (int *)take(4 * Ms);
     g.done = (int *)take(4 * Ms);
     g.where = (int *)take(4 * (Ms + Ns));

@@ -96,8 +96,6 @@ struct GridDev {
     int *pcols, *pwq; // compacted pivot row: pattern columns; mask word indices
     unsigned *pwb;    // ... and the mask words
     double *pvals;    // ... and the values
-    unsigned long long *colmax; // epoch: max |a_ij| of each remaining core column, as a bit pattern
-    int *colcnt, *colcand;      // ... how many rows attain it, and up to four of them
     int *rlast;                 // last column of each core row's nonzero pattern
     int *done;                  // back-substitution: component of this core column is final
     int *where;    // column -> nonbasic slot k >= 0, or -1 - (basis position)

@@ -1473,7 +1473,11 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
     {
         const int nq = core_nq(M);
         const size_t fixed = nq ? core_fixed_smem_bytes(M, Nn, nq) : 0;
-        const bool want = basis_home == 4;
+        // ... except for small batches of the wide classes (129 <= m_int <= 256, config 5's
+        // shape): with at most ~2.5 LPs per SM its low per-LP latency wins (measured: 296
+        // config-5 LPs 146 LP/s against 121 LP/s; 592 LPs 167 against 211)
+        const bool want = basis_home == 4 || (basis_home == 0 && warps_hint == 0 && cps_hint == 0 && M > 128 &&
+                                              B > 1 && B * 2 <= (int64_t)sms * 5);
         if (want && nq && M >= 1 && fixed + 1024 <= max_smem) {
             const size_t full = (size_t)M * (size_t)((M + 1) | 1) * 8;
             int cps = 1;
@@ -1500,9 +1504,9 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
             plan->core_mode = true;
             plan->core_cap_w = (int32_t)(cap_bytes / 8);
             plan->home = 4;
-            plan->worker_warps = nq <= 4 ? 3 : 7;
+            plan->worker_warps = nq <= 4 ? 3 : 15;
             plan->w_in_smem = cap_bytes >= full;
-            plan->block = nq <= 4 ? 128 : 256;
+            plan->block = nq <= 4 ? 128 : 512;
             plan->smem_bytes = (int32_t)(fixed + cap_bytes);
             plan->ctas_per_sm = cps;
             plan->gws_doubles_per_cta = (int64_t)((full + 15) / 8);

@@ -228,6 +228,7 @@ inline unsigned atomicExch(unsigned *p, unsigned v) {
     return old;
 }
 inline void __threadfence() {}
+inline void __threadfence_block() {}
 inline int atomicMin(int *p, int v) {
     const int old = *p;
     *p = std::min(old, v);

@@ -36,8 +36,8 @@ def tput(name, w, **kw):
     b.close()
 w2 = generate.config2(4096)
 for cps in (0, 2, 4):
-    tput("c2", w2, ctas_per_sm=cps)
+    tput("c2", w2, ctas_per_sm=cps, basis_home=4)
 tput("c2-warp", w2, worker_warps=-1)
 w5 = generate.config5(1184)
-tput("c5", w5)
+tput("c5", w5, basis_home=4)
 tput("c5-old", generate.config5(592), basis_home=2)

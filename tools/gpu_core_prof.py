@@ -5,7 +5,7 @@ import numpy as np
 from dantzig_b200 import generate, Template, Batch
 names = ["status", "lists", "gather", "elim", "back", "price", "ratio", "update"]
 def run(w, **kw):
-    b = Batch(Template(w.structure), w.B, profile=True, **kw)
+    b = Batch(Template(w.structure), w.B, profile=True, basis_home=4, **kw)
     b.upload(w.theta); b.solve(); r = b.download(light=True)
     ms = b.kernel_ms()
     p = r.prof.astype(np.float64)
