@@ -25,7 +25,7 @@ SYMBOLS = [
     "dz_template_create", "dz_template_destroy", "dz_template_get_info",
     "dz_template_get_arrays", "dz_template_pack_theta", "dz_options_default",
     "dz_solve_batch", "dz_solve_batch_multi", "dz_batch_create", "dz_batch_destroy", "dz_batch_upload",
-    "dz_batch_solve", "dz_batch_download", "dz_batch_sync", "dz_batch_last_timing",
+    "dz_batch_pack_dense", "dz_batch_solve", "dz_batch_download", "dz_batch_sync", "dz_batch_last_timing",
     "dz_batch_launch_info", "dz_batch_io_bytes", "dz_solve_model", "dz_last_error",
     "dz_device_count", "dz_device_info", "dz_version", "dz_measure_fp64_peak",
 ]
@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
     L.dz_options_default.argtypes = [C.POINTER(Options)]
     L.dz_options_default.restype = None
     L.dz_solve_batch.argtypes = [vp, i64, vp, C.POINTER(Options), C.POINTER(BatchResult)]
+    L.dz_batch_pack_dense.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32]
     L.dz_solve_batch_multi.argtypes = [vp, i64, vp, i32, C.POINTER(Options), C.POINTER(BatchResult)]
     L.dz_batch_create.argtypes = [vp, i64, C.POINTER(Options), C.POINTER(vp)]
     L.dz_batch_destroy.argtypes = [vp]

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #endif
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -134,6 +135,43 @@ struct dz_batch {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// dz_batch_pack_dense: one thread per element of theta (layout in include/dantzig_b200.h):
+// [1, c0, objective n, row coefficients n_low*n, rhs n_low, lb n, ub n].  row_src[r] is the user
+// row a lowered row comes from, with bit 31 set when it is negated.
+__global__ void dz_pack_dense_kernel(double *__restrict__ theta, const double *__restrict__ A,
+                                     const double *__restrict__ rhs, const double *__restrict__ c,
+                                     const int *__restrict__ row_src, const double *__restrict__ lbub,
+                                     long long B, int m, int n, int n_low, int minimize) {
+    const long long P = 2 + (long long)n + (long long)n_low * n + n_low + 2ll * n;
+    const long long total = B * P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long lp = e / P;
+        long long k = e - lp * P;
+        double v;
+        if (k == 0) {
+            v = 1.0;
+        } else if (k == 1) {
+            v = minimize ? -0.0 : 0.0;
+        } else if ((k -= 2) < n) {
+            const double cv = c[lp * n + k];
+            v = minimize ? -cv : cv;
+        } else if ((k -= n) < (long long)n_low * n) {
+            const int r = (int)(k / n), j = (int)(k - (long long)r * n);
+            const int src = row_src[r];
+            const double a = A[(lp * m + (src & 0x7fffffff)) * n + j];
+            v = src < 0 ? -a : a;
+        } else if ((k -= (long long)n_low * n) < n_low) {
+            const int src = row_src[k];
+            const double bv = rhs[lp * m + (src & 0x7fffffff)];
+            v = src < 0 ? -bv : bv;
+        } else {
+            v = lbub[k - n_low];
+        }
+        theta[e] = v;
+    }
+}
 
 extern "C" {
 
@@ -406,6 +444,92 @@ int dz_batch_upload(dz_batch *b, const double *theta) {
     DZ_CUDA(cudaSetDevice(b->opt.device));
     const size_t bytes = sizeof(double) * (size_t)b->B * (size_t)b->tmpl->host.n_theta;
     DZ_CUDA(cudaMemcpyAsync(b->d_theta, theta, bytes, cudaMemcpyHostToDevice, b->stream));
+    return DZ_OK;
+}
+
+int dz_batch_pack_dense(dz_batch *b, const double *A, const double *rhs, const double *c,
+                        const int32_t *senses, const double *lb, const double *ub, int32_t m,
+                        int32_t n, int32_t minimize, int32_t on_device) {
+    if (!b || !A || !rhs || !c || (m > 0 && !senses) || m < 0 || n <= 0) {
+        g_err = "dz_batch_pack_dense: bad argument";
+        return DZ_ERR_ARG;
+    }
+    std::vector<int> row_src;
+    for (int i = 0; i < m; ++i) {
+        if (senses[i] == 0 || senses[i] == 2) row_src.push_back(i);                     // <= row (also the first of ==)
+        if (senses[i] == 1 || senses[i] == 2) row_src.push_back(i | (int)0x80000000u);  // negated row
+        if (senses[i] < 0 || senses[i] > 2) {
+            g_err = "dz_batch_pack_dense: senses must be 0 (<=), 1 (>=) or 2 (==)";
+            return DZ_ERR_ARG;
+        }
+    }
+    const int n_low = (int)row_src.size();
+    const dz::Template &h = b->tmpl->host;
+    const int64_t P = 2 + (int64_t)n + (int64_t)n_low * n + n_low + 2 * (int64_t)n;
+    if (h.n_theta != P || h.n_vars != n || h.n_obj != n || h.n_rows_user != n_low ||
+        h.n_row_terms != (int64_t)n_low * n) {
+        g_err = "dz_batch_pack_dense: the batch's template is not the dense structure of this shape";
+        return DZ_ERR_ARG;
+    }
+    std::vector<double> lbub(2 * (size_t)n, 0.0);
+    for (int j = 0; j < n; ++j) {
+        if (lb && std::isfinite(lb[j])) lbub[(size_t)j] = lb[j];
+        if (ub && std::isfinite(ub[j])) lbub[(size_t)n + j] = ub[j];
+    }
+    DZ_CUDA(cudaSetDevice(b->opt.device));
+    const size_t nA = (size_t)b->B * m * n, nb = (size_t)b->B * m, nc = (size_t)b->B * n;
+    double *dA = nullptr, *db = nullptr, *dc = nullptr, *dl = nullptr;
+    int *dsrc = nullptr;
+    auto release = [&]() {
+        if (!on_device) {
+            cudaFree(dA);
+            cudaFree(db);
+            cudaFree(dc);
+        }
+        cudaFree(dl);
+        cudaFree(dsrc);
+    };
+    cudaError_t e = cudaSuccess;
+    if (on_device) {
+        dA = const_cast<double *>(A), db = const_cast<double *>(rhs), dc = const_cast<double *>(c);
+    } else {
+        if ((e = cudaMalloc(&dA, sizeof(double) * std::max<size_t>(nA, 1))) == cudaSuccess &&
+            (e = cudaMalloc(&db, sizeof(double) * std::max<size_t>(nb, 1))) == cudaSuccess &&
+            (e = cudaMalloc(&dc, sizeof(double) * nc)) == cudaSuccess) {
+            if (nA) cudaMemcpyAsync(dA, A, sizeof(double) * nA, cudaMemcpyHostToDevice, b->stream);
+            if (nb) cudaMemcpyAsync(db, rhs, sizeof(double) * nb, cudaMemcpyHostToDevice, b->stream);
+            cudaMemcpyAsync(dc, c, sizeof(double) * nc, cudaMemcpyHostToDevice, b->stream);
+        }
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&dl, sizeof(double) * lbub.size());
+    if (e == cudaSuccess) e = cudaMalloc(&dsrc, sizeof(int) * std::max<size_t>(row_src.size(), 1));
+    if (e != cudaSuccess) {
+        release();
+        cudaGetLastError();
+        g_err = "dz_batch_pack_dense: cudaMalloc failed";
+        return DZ_ERR_ALLOC;
+    }
+    cudaMemcpyAsync(dl, lbub.data(), sizeof(double) * lbub.size(), cudaMemcpyHostToDevice, b->stream);
+    if (n_low) cudaMemcpyAsync(dsrc, row_src.data(), sizeof(int) * row_src.size(), cudaMemcpyHostToDevice, b->stream);
+    const long long total = (long long)b->B * P;
+    const int block = 256;
+    const int grid = (int)std::min<long long>((total + block - 1) / block, 148 * 16);
+#ifdef DZ_EMU
+    cudaStreamSynchronize(b->stream);
+    emu::launch(dz_pack_dense_kernel, std::min(grid, 4), 64, (size_t)0, b->d_theta, (const double *)dA, (const double *)db,
+                (const double *)dc, (const int *)dsrc, (const double *)dl, (long long)b->B, (int)m, (int)n, n_low,
+                (int)minimize);
+#else
+    dz_pack_dense_kernel<<<grid, block, 0, b->stream>>>(b->d_theta, dA, db, dc, dsrc, dl, (long long)b->B, m, n, n_low,
+                                                        minimize);
+    e = cudaGetLastError();
+#endif
+    cudaStreamSynchronize(b->stream); // the staging buffers and the host vectors above go out of scope
+    release();
+    if (e != cudaSuccess) {
+        g_err = std::string("dz_pack_dense_kernel: ") + cudaGetErrorString(e);
+        return DZ_ERR_CUDA;
+    }
     return DZ_OK;
 }
 

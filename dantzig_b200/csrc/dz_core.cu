@@ -700,8 +700,11 @@ __device__ __forceinline__ void core_hand_over(Core &c, const BatchDev &Bt, long
     for (int i = c.tid; i < Nn; i += c.NT) si[M + i] = c.nb[i];
 }
 
-template <int NQ>
-__global__ void __launch_bounds__(NQ <= 4 ? 128 : 512, NQ <= 4 ? 3 : 1)
+// NTH threads per CTA: 128 for m_int <= 128 (3-4 CTAs per SM); for the wide classes 512 (one CTA
+// per SM, the whole core in shared memory) or 256 (two CTAs per SM, part of the core's rows in the
+// HBM/L2 workspace).
+template <int NQ, int NTH>
+__global__ void __launch_bounds__(NTH, NTH == 128 ? 3 : (NTH == 256 ? 2 : 1))
 dz_core_kernel(const TemplateDev T, const BatchDev Bt, const int capW) {
 #ifdef DZ_EMU
     unsigned char *smem_raw = emu::dyn_smem();
@@ -1034,10 +1037,10 @@ int core_nq(int M) {
     return 0;
 }
 
-template <int NQ>
+template <int NQ, int NTH>
 static cudaError_t launch_core_one(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan,
                                    cudaStream_t st) {
-    auto kern = dz_core_kernel<NQ>;
+    auto kern = dz_core_kernel<NQ, NTH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
     if (e != cudaSuccess) return e;
 #ifdef DZ_EMU
@@ -1054,12 +1057,12 @@ int launch_core(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     switch (core_nq(T.M)) {
-    case 1: e = launch_core_one<1>(T, Bt, plan, st); break;
-    case 2: e = launch_core_one<2>(T, Bt, plan, st); break;
-    case 3: e = launch_core_one<3>(T, Bt, plan, st); break;
-    case 4: e = launch_core_one<4>(T, Bt, plan, st); break;
-    case 6: e = launch_core_one<6>(T, Bt, plan, st); break;
-    case 8: e = launch_core_one<8>(T, Bt, plan, st); break;
+    case 1: e = launch_core_one<1, 128>(T, Bt, plan, st); break;
+    case 2: e = launch_core_one<2, 128>(T, Bt, plan, st); break;
+    case 3: e = launch_core_one<3, 128>(T, Bt, plan, st); break;
+    case 4: e = launch_core_one<4, 128>(T, Bt, plan, st); break;
+    case 6: e = plan.block == 256 ? launch_core_one<6, 256>(T, Bt, plan, st) : launch_core_one<6, 512>(T, Bt, plan, st); break;
+    case 8: e = plan.block == 256 ? launch_core_one<8, 256>(T, Bt, plan, st) : launch_core_one<8, 512>(T, Bt, plan, st); break;
     default:
         *err = "dz_core_kernel: m_int > 256";
         return DZ_ERR_LIMIT;

@@ -1476,8 +1476,9 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
         // ... except for small batches of the wide classes (129 <= m_int <= 256, config 5's
         // shape): with at most ~2.5 LPs per SM its low per-LP latency wins (measured: 296
         // config-5 LPs 146 LP/s against 121 LP/s; 592 LPs 167 against 211)
-        const bool want = basis_home == 4 || (basis_home == 0 && warps_hint == 0 && cps_hint == 0 && M > 128 &&
-                                              B > 1 && B * 2 <= (int64_t)sms * 5);
+        const bool small_wide = basis_home == 0 && warps_hint == 0 && cps_hint == 0 && M > 128 && B > 1 &&
+                                B * 2 <= (int64_t)sms * 5;
+        const bool want = basis_home == 4 || small_wide;
         if (want && nq && M >= 1 && fixed + 1024 <= max_smem) {
             const size_t full = (size_t)M * (size_t)((M + 1) | 1) * 8;
             int cps = 1;
@@ -1495,6 +1496,9 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
                 }
                 const int64_t need = (B + sms - 1) / sms;
                 if (need < cps) cps = (int)std::max<int64_t>(need, 1);
+                // wide classes: a second CTA per SM (256 threads each, part of the core's rows in
+                // the workspace) beats a second wave: 296 config-5 LPs 1.64 s against 2.03 s
+                if (nq > 4 && B > sms) cps = 2;
             }
             cps = std::max(1, std::min(cps, 16));
             size_t per_cta = std::min<size_t>(per_sm / cps - 1024, max_smem);
@@ -1504,9 +1508,9 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
             plan->core_mode = true;
             plan->core_cap_w = (int32_t)(cap_bytes / 8);
             plan->home = 4;
-            plan->worker_warps = nq <= 4 ? 3 : 15;
+            plan->worker_warps = nq <= 4 ? 3 : (cps >= 2 ? 7 : 15);
             plan->w_in_smem = cap_bytes >= full;
-            plan->block = nq <= 4 ? 128 : 512;
+            plan->block = nq <= 4 ? 128 : (cps >= 2 ? 256 : 512);
             plan->smem_bytes = (int32_t)(fixed + cap_bytes);
             plan->ctas_per_sm = cps;
             plan->gws_doubles_per_cta = (int64_t)((full + 15) / 8);
@@ -1520,7 +1524,11 @@ int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32
     // Auto: one warp per LP when the batch is large enough to fill the machine with
     // independent warps and the fast small-M step applies; measured on config 2:
     // 8.4 kLP/s (32 warps/SM) vs 5.3 kLP/s CTA-per-LP (profiles/).
-    const bool auto_warp = warps_hint == 0 && basis_home == 0 && M <= 128 && B >= (int64_t)sms * 8;
+    // ... and for the wide classes (config 5) once the batch fills its 16 warps per SM: measured
+    // 4736 LPs 465 LP/s against 414 (CTA per LP); 1184 LPs 317 against 368, so smaller batches
+    // stay with the CTA shape (and the smallest go to the core kernel above).
+    const bool auto_warp = warps_hint == 0 && basis_home == 0 &&
+                           ((M <= 128 && B >= (int64_t)sms * 8) || (M > 128 && M <= 256 && B >= (int64_t)sms * 12));
     if ((warps_hint < 0 || auto_warp) && without <= max_smem / 2 && M <= 1024) {
         // warp-per-LP: WPC independent warps per CTA, basis in the HBM workspace
         const size_t per_team =

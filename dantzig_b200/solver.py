@@ -145,6 +145,27 @@ class Batch:
         """Upload from a raw host pointer (e.g. pinned memory owned by the caller)."""
         _capi.check(_capi.lib().dz_batch_upload(self._h, C.c_void_p(ptr)))
 
+    def pack_dense(self, A, b, c, senses, lb=None, ub=None, *, minimize: bool = True, on_device: bool = False) -> None:
+        """dz_batch_pack_dense: the batch's parameter vectors written on the device from the plain
+        user-level arrays (host numpy arrays, or raw device pointers when on_device)."""
+        senses = np.ascontiguousarray(senses, dtype=np.int32)
+        m = len(senses)
+        if on_device:
+            pa, pb, pc = (C.c_void_p(int(x)) for x in (A, b, c))
+            n = self.template.n_orig
+        else:
+            A = np.ascontiguousarray(A, dtype=np.float64).reshape(self.B, m, -1)
+            n = A.shape[2]
+            b = np.ascontiguousarray(b, dtype=np.float64).reshape(self.B, m)
+            c = np.ascontiguousarray(c, dtype=np.float64).reshape(self.B, n)
+            self._dense_keep = (A, b, c)
+            pa, pb, pc = _vp(A), _vp(b), _vp(c)
+        lbv = None if lb is None else np.ascontiguousarray(lb, dtype=np.float64)
+        ubv = None if ub is None else np.ascontiguousarray(ub, dtype=np.float64)
+        _capi.check(_capi.lib().dz_batch_pack_dense(
+            self._h, pa, pb, pc, _vp(senses), None if lbv is None else _vp(lbv),
+            None if ubv is None else _vp(ubv), m, n, 1 if minimize else 0, 1 if on_device else 0))
+
     def solve(self) -> None:
         _capi.check(_capi.lib().dz_batch_solve(self._h))
 
@@ -290,7 +311,7 @@ def solve_dense_batch(A, b, c, senses, lb=None, ub=None, *, minimize: bool = Tru
     reference frontend lowers the same model (see model.py), solved on the GPU.
     Returns (status[B], objective[B] in the caller's sense, x[B, n], BatchResult).
     """
-    from .model import dense_structure, dense_theta
+    from .model import dense_structure
 
     A = np.asarray(A, dtype=np.float64)
     if A.ndim == 2:
@@ -300,9 +321,13 @@ def solve_dense_batch(A, b, c, senses, lb=None, ub=None, *, minimize: bool = Tru
     ub = np.full(n, np.inf) if ub is None else np.asarray([np.inf if v is None else v for v in ub], float)
     has_lb, has_ub = np.isfinite(lb), np.isfinite(ub)
     structure = dense_structure(m, n, senses, has_lb, has_ub)
-    theta = dense_theta(A, np.asarray(b, float).reshape(B, m), np.asarray(c, float).reshape(B, n),
-                        senses, np.where(has_lb, lb, 0.0), np.where(has_ub, ub, 0.0), has_lb, has_ub,
-                        minimize=minimize)
-    res = solve_batch(Template(structure), theta, **kw)
+    # the numbers are lowered on the device (dz_batch_pack_dense): no host-side theta
+    batch = Batch(Template(structure), B, **kw)
+    try:
+        batch.pack_dense(A, b, c, senses, np.where(has_lb, lb, 0.0), np.where(has_ub, ub, 0.0), minimize=minimize)
+        batch.solve()
+        res = batch.download()
+    finally:
+        batch.close()
     objective = -res.objective if minimize else res.objective
     return res.status, objective, res.values, res

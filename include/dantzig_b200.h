@@ -177,6 +177,19 @@ typedef struct dz_batch dz_batch;
 int dz_batch_create(const dz_template *t, int64_t B, const dz_options *opt, dz_batch **out);
 void dz_batch_destroy(dz_batch *b);
 int dz_batch_upload(dz_batch *b, const double *theta);        /* H2D, async on the stream */
+/* Array-native front door with the lowering of the NUMBERS on the device:
+ * B dense user-level LPs of one shape,  min/max c.x  s.t.  A x (senses) rhs,  lb <= x <= ub,  in
+ * plain arrays A[B][m][n], rhs[B][m], c[B][n] (HOST memory when on_device == 0, DEVICE memory on
+ * the batch's device otherwise), senses[m] in {0: <=, 1: >=, 2: ==} and lb/ub[n] on the host
+ * (shared by the batch; ignored where the template's variable has no such bound).  A kernel
+ * writes the batch's parameter vectors straight into HBM the way the reference frontend lowers
+ * the same model (>= rows negated, == rows as the <= row followed by the negated row,
+ * model.py:351-375; Minimize negates the objective, optimize.py:115): no host-side theta.
+ * The template must come from the matching dense structure (every row and the objective mention
+ * every variable in index order). */
+int dz_batch_pack_dense(dz_batch *b, const double *A, const double *rhs, const double *c,
+                        const int32_t *senses, const double *lb, const double *ub, int32_t m,
+                        int32_t n, int32_t minimize, int32_t on_device);
 int dz_batch_solve(dz_batch *b);                               /* launch, async            */
 int dz_batch_download(dz_batch *b, dz_batch_result *out);      /* D2H + synchronize        */
 int dz_batch_sync(dz_batch *b);

@@ -181,6 +181,42 @@ def test_array_native_front_door():
             assert {0: 0, 2: 2, 3: 1}.get(ref.status, -1) == status[i]
 
 
+def test_pack_dense_on_device_equals_host_theta():
+    """dz_batch_pack_dense (the numbers lowered by a kernel from plain A, b, c) gives the very
+    parameter vectors the host-side packing gives: same results bit for bit, mixed row senses,
+    boxed / free variables, both objective senses."""
+    from dantzig_b200 import EQ, GE, LE, dense_structure, dense_theta
+
+    rng = np.random.default_rng(11)
+    B, m, n = 24, 7, 10
+    A = rng.uniform(-1, 1, (B, m, n))
+    x0 = rng.uniform(0.2, 0.8, (B, n))
+    senses = np.array([LE, GE, EQ, LE, GE, LE, EQ], np.int32)
+    b = np.einsum("bij,bj->bi", A, x0) + np.where(senses == LE, 0.3, np.where(senses == GE, -0.3, 0.0))
+    c = rng.uniform(-1, 1, (B, n))
+    has_lb = np.array([j % 4 != 3 for j in range(n)])
+    has_ub = np.array([j % 3 == 0 for j in range(n)])
+    lb, ub = np.where(has_lb, 0.0, 0.0), np.where(has_ub, 1.0, 0.0)
+    st = dense_structure(m, n, senses, has_lb, has_ub)
+    t = Template(st)
+    for minimize in (True, False):
+        ref = solve_batch(t, dense_theta(A, b, c, senses, lb, ub, has_lb, has_ub, minimize=minimize), trace_cap=32)
+        bt = Batch(t, B, trace_cap=32)
+        bt.pack_dense(A, b, c, senses, lb, ub, minimize=minimize)
+        bt.solve()
+        got = bt.download()
+        bt.close()
+        for name in ("status", "pivots", "trace_hash", "objective", "values", "x_basic", "basis", "trace"):
+            a1, a2 = getattr(ref, name), getattr(got, name)
+            assert np.array_equal(a1, a2, equal_nan=a1.dtype.kind == "f"), (minimize, name)
+    with pytest.raises(Exception):                       # a template of another shape is refused
+        bt = Batch(Template(dense_structure(m, n + 1, senses, np.ones(n + 1, bool), np.zeros(n + 1, bool))), B)
+        try:
+            bt.pack_dense(A, b, c, senses, lb, ub)
+        finally:
+            bt.close()
+
+
 def test_empty_basis_is_breakdown():
     from dantzig_b200.model import ModelBuilder
 
