@@ -242,14 +242,17 @@ def measured_peaks() -> dict:
         return {}
 
 
-def recorded_traffic(kernel_tag: str):
-    """DRAM bytes per launch from the committed ncu capture -- only if that capture was taken
-    on the library that is loaded now and on this kernel/workload (profiles/traffic.json)."""
+def recorded_traffic(tag: str, units: float, prefix: int | None = None):
+    """DRAM bytes per launch from the committed ncu capture of this workload's kernel -- only if
+    that capture was taken on the very library that is loaded now (profiles/traffic.json holds
+    bytes per LP, or per launch of a pivot prefix, with the library hash)."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         for e in t.get("captures", []):
-            if e.get("lib_sha16") == _lib_sha16() and e.get("tag") == kernel_tag:
-                return e["dram_bytes_per_launch"]
+            if e.get("lib_sha16") == _lib_sha16() and e.get("tag") == tag:
+                if e.get("prefix") is not None:
+                    return e["dram_bytes_per_unit"] if prefix == e["prefix"] else None
+                return e["dram_bytes_per_unit"] * units
     except Exception:
         pass
     return None
@@ -392,7 +395,7 @@ def run_gpu(args) -> None:
             alg_bytes = 16.0 * core_doubles + 12.0 * float(res.work[0, 2]) / 2.0 + 48.0 * (M + Nn) * pivots_rank
             ach = alg_bytes / (ms_step * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": recorded_traffic(args.workload),
+                    "traffic": recorded_traffic(args.workload, 1, args.prefix),
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "note": "algorithmic bytes = 16 B x doubles of working core cleared+filled over all solves "
                             "+ 12 B x priced entries + 48 B x (m_int + n_nonbasic) x pivots; the kernel is bound by "
@@ -406,7 +409,7 @@ def run_gpu(args) -> None:
             flops_literal = pivots_rank * (4.0 / 3.0 * M ** 3 + 4.0 * M ** 2 + 2.0 * nnz_n)
             alg_bytes = h2d + d2h
             roof = {"bound": "fp64", "achieved": ach_tf, "peak": mul_sub / 1e3, "unit": "TFLOP/s",
-                    "frac": ach_tf / (mul_sub / 1e3), "traffic": recorded_traffic(args.workload),
+                    "frac": ach_tf / (mul_sub / 1e3), "traffic": recorded_traffic(args.workload, units_rank),
                     "note": "the exact path is un-fused FP64 vector work (no tensor/HBM bound applies); peak = "
                             "un-fused DMUL+DSUB rate measured live by dz_measure_fp64_peak (fused DFMA rate "
                             f"{fma / 1e3:.1f} TFLOP/s); achieved = EXECUTED flops (exact-zero work skipped) / kernel time",

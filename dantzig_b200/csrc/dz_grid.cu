@@ -77,6 +77,7 @@ struct G {
     double *sbuf;  // [kBufTerms]
     unsigned long long *wmax; // [kWin] window: column maxima as bit patterns
     int *wcnt, *wcand;        // [kWin], [4 kWin]: rows attaining them
+    int *wgid, *winert;       // [4 kWin] each: the candidates' system rows; whether a step they win changes nothing
     int *heap;                // [kHeapCap] min-heap of disturbed positions; size in sctl[10], overflow in sctl[11]
     int parity;
     unsigned long long n_lu, n_solve, n_price;
@@ -775,7 +776,8 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
                     if (lo > 0) word = lo >= 32 ? 0u : (word & ~((1u << lo) - 1u));
                     if (hi < 32) word = hi <= 0 ? 0u : (word & ((1u << hi) - 1u));
                     if (!word) continue; // nothing of this row in this part of the window
-                    if (D.posOf[rlist[i]] < k) continue;
+                    const int gid = rlist[i];
+                    if (D.posOf[gid] < k) continue;
                     const double *__restrict__ row = D.W + (size_t)i * S;
                     while (word) { // eight independent loads at a time
                         int jj[8];
@@ -803,7 +805,12 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
                                 if (key > *((volatile unsigned long long *)&g.wmax[slot_j])) atomicMax(&g.wmax[slot_j], key);
                             } else if (key == g.wmax[slot_j]) {
                                 const int slot = atomicAdd(&g.wcnt[slot_j], 1);
-                                if (slot < 4) g.wcand[4 * slot_j + slot] = i;
+                                if (slot < 4) {
+                                    // everything a commit needs to know about this candidate
+                                    g.wcand[4 * slot_j + slot] = i;
+                                    g.wgid[4 * slot_j + slot] = gid;
+                                    g.winert[4 * slot_j + slot] = (D.rlast[i] <= jj[e] && row[nr] == 0.0) ? 1 : 0;
+                                }
                             }
                         }
                     }
@@ -887,13 +894,13 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
                         const int cnt = g.wcnt[cc - epoch_lo];
                         if (cnt >= 1 && cnt <= 4) {
                             const int row = lane < cnt ? g.wcand[4 * (cc - epoch_lo) + lane] : -1;
-                            int pos = row >= 0 ? D.posOf[rlist[row]] : 0x7fffffff;
+                            int pos = row >= 0 ? D.posOf[g.wgid[4 * (cc - epoch_lo) + lane]] : 0x7fffffff;
                             if (pos < k) pos = 0x7fffffff; // that candidate has been used up since
                             const int best = __reduce_min_sync(kFull, pos);
                             if (best != 0x7fffffff) {
                                 const int src = __ffs(__ballot_sync(kFull, pos == best)) - 1;
                                 const int pr = __shfl_sync(kFull, row, src);
-                                const bool inert = D.rlast[pr] <= cc && D.W[(size_t)pr * S + nr] == 0.0;
+                                const bool inert = g.winert[4 * (cc - epoch_lo) + src] != 0;
                                 if (inert) {
                                     if (lane == 0) {
                                         g_swap_pos(g, D, k, best); // linalg.rs:107-114
@@ -938,12 +945,29 @@ __device__ __forceinline__ bool grid_solve(G &g, const GridDev &D, const Templat
         cd.key[0] = 0.0;
         cd.idx[0] = -1; // idx = position (unique per row)
         bool bad = false;
-        for (int i = tid; i < nr; i += g.NT) {
-            // only rows whose pattern has this column can hold a nonzero there
-            if (!((D.rmask[(size_t)i * MW + (cc >> 5)] >> (cc & 31)) & 1u)) continue;
-            const int pos = D.posOf[rlist[i]];
-            if (pos >= k) {
-                const double v = D.W[(size_t)i * S + cc];
+        for (int base = tid; base < nr; base += 8 * g.NT) {
+            // only rows whose pattern has this column can hold a nonzero there; eight rows per trip
+            // so that mask words, row ids, positions and values are batches of independent loads
+            bool on[8];
+            int gid8[8], pos8[8];
+            double v8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int i = base + e * g.NT;
+                on[e] = i < nr && ((D.rmask[(size_t)i * MW + (cc >> 5)] >> (cc & 31)) & 1u);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) gid8[e] = on[e] ? rlist[base + e * g.NT] : 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                pos8[e] = on[e] ? D.posOf[gid8[e]] : -1;
+                v8[e] = on[e] ? D.W[(size_t)(base + e * g.NT) * S + cc] : 0.0;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (!on[e] || pos8[e] < k) continue;
+                const int i = base + e * g.NT, pos = pos8[e];
+                const double v = v8[e];
                 bad = bad || !isfinite(v);
                 if (v != 0.0) {
                     const double av = fabs(v);
@@ -1141,6 +1165,8 @@ dz_grid_kernel(const TemplateDev T, const BatchDev Bt, const GridDev D) {
         g.heap = ip, ip += kHeapCap;
         g.wcnt = ip, ip += kWin;
         g.wcand = ip, ip += 4 * kWin;
+        g.wgid = ip, ip += 4 * kWin;
+        g.winert = ip, ip += 4 * kWin;
         g.prof = (Bt.prof && g.blk == 0) ? reinterpret_cast<long long *>(ip) : nullptr;
     }
     const int M = g.M, Nn = g.Nn, tid = g.tid;
@@ -1459,7 +1485,7 @@ size_t grid_workspace(int M, int Nn, long long nnz, int nblocks, long long w_cap
 }
 
 size_t grid_smem_bytes() {
-    return (size_t)kBufTerms * 8 + kWin * 8 + 2 * 4 * kMaxWarps * 8 + (2 * 4 * kMaxWarps + 4 * kMaxWarps + 16 + 5 * kWin + kHeapCap) * 4 + 16 * 8 + 16;
+    return (size_t)kBufTerms * 8 + kWin * 8 + 2 * 4 * kMaxWarps * 8 + (2 * 4 * kMaxWarps + 4 * kMaxWarps + 16 + 13 * kWin + kHeapCap) * 4 + 16 * 8 + 16;
 }
 
 int launch_grid(const TemplateDev &T, const BatchDev &Bt, const GridDev &D, const LaunchPlan &plan, void *stream,
