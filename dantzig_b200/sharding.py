@@ -30,6 +30,8 @@ def gather_results(local: dict[str, np.ndarray], n_lps: int, dist=None, device=N
     world, rank = dist.get_world_size(), dist.get_rank()
     sizes = [shard_range(n_lps, r, world) for r in range(world)]
     cap = max(hi - lo for lo, hi in sizes)
+    if cap == 0:  # an empty batch: nothing to exchange
+        return {k: np.asarray(v) for k, v in local.items()}
     out = {}
     for name, arr in local.items():
         arr = np.ascontiguousarray(arr)
