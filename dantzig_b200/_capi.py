@@ -18,6 +18,7 @@ if os.environ.get("DZ_LIB") and os.environ.get("DZ_LIB_TEST_ONLY") == "1":
 
 OK, ERR_ARG, ERR_CUDA, ERR_LIMIT, ERR_ALLOC = 0, -1, -2, -3, -4
 OPTIMAL, UNBOUNDED, INFEASIBLE, BREAKDOWN, PIVOT_CAP = range(5)
+NUMERICS_EXACT, NUMERICS_FAST = 0, 1
 STATUS_NAMES = ["optimal", "unbounded", "infeasible", "breakdown", "pivot_cap"]
 
 # every symbol include/dantzig_b200.h declares (tests check the export list)
@@ -62,7 +63,7 @@ class Options(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("max_pivots", C.c_int64), ("trace_cap", C.c_int32),
         ("worker_warps", C.c_int32), ("ctas_per_sm", C.c_int32), ("stream", C.c_void_p),
-        ("profile", C.c_int32), ("basis_home", C.c_int32),
+        ("profile", C.c_int32), ("basis_home", C.c_int32), ("numerics", C.c_int32),
     ]
 
 

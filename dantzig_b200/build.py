@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "--fmad=false",
     "-Xcompiler", "-fPIC",
 ]
-LIB_SOURCES = ["dz_kernel.cu", "dz_core.cu", "dz_grid.cu", "dz_capi.cu", "dz_lower.cpp"]
+LIB_SOURCES = ["dz_kernel.cu", "dz_core.cu", "dz_grid.cu", "dz_fast.cu", "dz_capi.cu", "dz_lower.cpp"]
 LIB_HEADERS = ["dz_internal.h", "dz_device.cuh", os.path.join("..", "..", "include", "dantzig_b200.h")]
 
 

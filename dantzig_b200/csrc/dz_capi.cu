@@ -72,6 +72,20 @@ static int template_on_device(dz_template *t, int device, dz::TemplateDev *view)
     const size_t o_c = push(h.c_ref), o_b = push(h.b_ref), o_b0 = push(h.basis0);
     const size_t o_n0 = push(h.nonbasis0), o_pi = push(h.pos_index), o_ni = push(h.neg_index);
     const size_t o_sr = push(h.slack_row), o_tw = push(h.twin);
+    // row-major view of the pattern (fast-numerics kernel): entries of a row in ascending column order
+    std::vector<int32_t> csr_ptr((size_t)h.m + 1, 0), csr_col(nnz), csr_ref(nnz);
+    for (size_t e = 0; e < nnz; ++e) csr_ptr[(size_t)h.row_idx[e] + 1]++;
+    for (int32_t r = 0; r < h.m; ++r) csr_ptr[(size_t)r + 1] += csr_ptr[(size_t)r];
+    {
+        std::vector<int32_t> fill(csr_ptr.begin(), csr_ptr.end() - 1);
+        for (int32_t col = 0; col < h.n_int; ++col)
+            for (int64_t e = h.col_ptr[(size_t)col]; e < h.col_ptr[(size_t)col + 1]; ++e) {
+                const int32_t at = fill[(size_t)h.row_idx[(size_t)e]]++;
+                csr_col[(size_t)at] = col;
+                csr_ref[(size_t)at] = h.val_ref[(size_t)e];
+            }
+    }
+    const size_t o_rp = push(csr_ptr), o_rc = push(csr_col), o_rr = push(csr_ref);
     DZ_CUDA(cudaSetDevice(device));
     dz_template::Dev d;
     d.device = device;
@@ -97,6 +111,9 @@ static int template_on_device(dz_template *t, int device, dz::TemplateDev *view)
     d.view.neg_index = d.blob + o_ni;
     d.view.slack_row = d.blob + o_sr;
     d.view.twin = d.blob + o_tw;
+    d.view.csr_ptr = d.blob + o_rp;
+    d.view.csr_col = d.blob + o_rc;
+    d.view.csr_ref = d.blob + o_rr;
     t->devs.push_back(d);
     *view = d.view;
     return DZ_OK;
@@ -297,9 +314,15 @@ int dz_batch_create(const dz_template *tc, int64_t B, const dz_options *opt, dz_
     rc = template_on_device(t, b->opt.device, &b->tview);
     if (rc != DZ_OK) return fail(rc);
     const dz::Template &h = t->host;
-    rc = dz::plan_launch(b->opt.device, h.m, h.n_int - h.m, (int64_t)h.row_idx.size(), B,
-                         b->opt.worker_warps,
-                         b->opt.ctas_per_sm, b->opt.basis_home, &b->plan, &g_err);
+    if (b->opt.numerics == DZ_NUMERICS_FAST)
+        rc = dz::plan_fast(b->opt.device, h.m, h.n_int - h.m, h.n_int, B, b->opt.ctas_per_sm, &b->plan, &g_err);
+    else if (b->opt.numerics != DZ_NUMERICS_EXACT) {
+        g_err = "dz_batch_create: options.numerics must be DZ_NUMERICS_EXACT or DZ_NUMERICS_FAST";
+        rc = DZ_ERR_ARG;
+    } else
+        rc = dz::plan_launch(b->opt.device, h.m, h.n_int - h.m, (int64_t)h.row_idx.size(), B,
+                             b->opt.worker_warps,
+                             b->opt.ctas_per_sm, b->opt.basis_home, &b->plan, &g_err);
     if (rc != DZ_OK) return fail(rc);
     if (b->opt.stream) {
         b->stream = (cudaStream_t)b->opt.stream;
@@ -549,7 +572,9 @@ int dz_batch_solve(dz_batch *b) {
                                 sizeof(double) * (size_t)b->plan.gws_doubles_per_cta *
                                     (size_t)b->plan.teams, b->stream));
     int rc;
-    if (b->plan.grid_mode) {
+    if (b->plan.fast_mode) {
+        rc = dz::launch_fast(b->tview, b->bd, b->plan, b->stream, &g_err);
+    } else if (b->plan.grid_mode) {
         DZ_CUDA(cudaMemsetAsync(b->grid.bar, 0, 4 * sizeof(unsigned), b->stream));
         rc = dz::launch_grid(b->tview, b->bd, b->grid, b->plan, b->stream, &g_err);
     } else {
@@ -742,7 +767,7 @@ constexpr size_t kModelCacheEntries = 8;
 bool same_options(const dz_options &a, const dz_options &b) {
     return a.device == b.device && a.max_pivots == b.max_pivots && a.trace_cap == b.trace_cap &&
            a.worker_warps == b.worker_warps && a.ctas_per_sm == b.ctas_per_sm && a.stream == b.stream &&
-           a.profile == b.profile && a.basis_home == b.basis_home;
+           a.profile == b.profile && a.basis_home == b.basis_home && a.numerics == b.numerics;
 }
 } // namespace
 

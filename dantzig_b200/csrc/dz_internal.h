@@ -50,6 +50,10 @@ struct TemplateDev {
     const int32_t *neg_index; // [n_orig]
     const int32_t *slack_row; // [Nint]
     const int32_t *twin;      // [Nint]
+    // row-major (CSR) view of the same pattern, used by the fast-numerics kernel (dz_fast.cu)
+    const int32_t *csr_ptr;   // [M+1]
+    const int32_t *csr_col;   // [nnz]
+    const int32_t *csr_ref;   // [nnz]
 };
 
 // Device view of one batch: inputs and outputs, all in HBM.
@@ -117,6 +121,7 @@ struct LaunchPlan {
     bool grid_mode = false;    // whole-GPU single-LP kernel (dz_grid.cu), cooperative launch
     bool core_mode = false;    // on-chip coupled-core kernel (dz_core.cu)
     int32_t core_cap_w = 0;    // its shared-memory capacity for the working core, in doubles
+    bool fast_mode = false;    // opt-in fast numerics (dz_fast.cu); core_cap_w = capacity for K
 };
 
 int plan_launch(int device, int32_t M, int32_t Nn, int64_t nnz, int64_t B, int32_t warps_hint,
@@ -129,6 +134,10 @@ size_t core_fixed_smem_bytes(int M, int Nn, int NQ);
 int core_nq(int M); // rows-per-lane class of the core kernel (0: m_int too large for it)
 int launch_core(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan, void *stream,
                 std::string *err);
+// dz_fast.cu (opt-in fast numerics, dz_options.numerics == DZ_NUMERICS_FAST)
+int plan_fast(int device, int32_t M, int32_t Nn, int32_t Nint, int64_t B, int32_t cps_hint, LaunchPlan *plan,
+              std::string *err);
+int launch_fast(const TemplateDev &T, const BatchDev &Bt, const LaunchPlan &plan, void *stream, std::string *err);
 // dz_grid.cu
 size_t grid_workspace(int M, int Nn, long long nnz, int nblocks, long long w_cap_doubles, unsigned char *base,
                       GridDev *d);

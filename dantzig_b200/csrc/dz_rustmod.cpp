@@ -245,7 +245,12 @@ Solution solve(const AffExpr &objective, const std::vector<Inequality> &constrai
 // result list holds, per LP and in input order, a PySolution or the exception
 // instance solve() would have raised (returned, not raised).
 py::list solve_batch(const std::vector<AffExpr> &objectives,
-                     const std::vector<std::vector<Inequality>> &constraints, int n_gpus) {
+                     const std::vector<std::vector<Inequality>> &constraints, int n_gpus,
+                     const std::string &numerics) {
+    // numerics: "exact" (default, the reference's floating-point order) or "fast" (opt-in,
+    // DZ_NUMERICS_FAST: agrees with the reference to rounding only)
+    if (numerics != "exact" && numerics != "fast")
+        throw py::value_error("solve_batch: numerics must be \"exact\" or \"fast\"");
     if (objectives.size() != constraints.size())
         throw py::value_error("solve_batch: objectives and constraints differ in length");
     const std::size_t n = objectives.size();
@@ -273,6 +278,7 @@ py::list solve_batch(const std::vector<AffExpr> &objectives,
         py::gil_scoped_release release;
         dz_options opt;
         dz_options_default(&opt);
+        opt.numerics = numerics == "fast" ? DZ_NUMERICS_FAST : DZ_NUMERICS_EXACT;
         for (const auto &k : keys) {
             const auto &members = groups[k];
             const std::size_t B = members.size();
@@ -401,5 +407,6 @@ PYBIND11_MODULE(rust, m) {
         });
 
     m.def("solve", &solve, py::arg("objective"), py::arg("constraints"));
-    m.def("solve_batch", &solve_batch, py::arg("objectives"), py::arg("constraints"), py::arg("n_gpus") = 1);
+    m.def("solve_batch", &solve_batch, py::arg("objectives"), py::arg("constraints"), py::arg("n_gpus") = 1,
+          py::arg("numerics") = "exact");
 }

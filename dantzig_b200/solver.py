@@ -97,12 +97,15 @@ class BatchResult:
 
 
 def _options(device=0, max_pivots=0, trace_cap=0, worker_warps=0, ctas_per_sm=0, stream=None,
-             profile=False, basis_home=0):
+             profile=False, basis_home=0, numerics="exact"):
     o = _capi.Options()
     _capi.lib().dz_options_default(C.byref(o))
     o.device, o.max_pivots, o.trace_cap = int(device), int(max_pivots), int(trace_cap)
     o.worker_warps, o.ctas_per_sm = int(worker_warps), int(ctas_per_sm)
     o.basis_home = int(basis_home)
+    # "exact" (default): the reference's floating-point order, bit-identical pivot sequences;
+    # "fast": OPT-IN fast numerics (dz_fast.cu), agrees to rounding only
+    o.numerics = {"exact": _capi.NUMERICS_EXACT, "fast": _capi.NUMERICS_FAST}[numerics]
     o.stream = stream
     o.profile = 1 if profile else 0
     return o
@@ -114,12 +117,12 @@ class Batch:
     def __init__(self, template: Template, B: int, *, device: int = 0, max_pivots: int = 0,
                  trace_cap: int = 0, worker_warps: int = 0, ctas_per_sm: int = 0,
                  stream: int | None = None, want_basis: bool = False, profile: bool = False,
-                 basis_home: int = 0):
+                 basis_home: int = 0, numerics: str = "exact"):
         self.template, self.B = template, int(B)
         self.trace_cap, self.want_basis, self.profile = int(trace_cap), want_basis, profile
         self._h = C.c_void_p()
         o = _options(device, max_pivots, trace_cap, worker_warps, ctas_per_sm,
-                     stream, profile, basis_home)
+                     stream, profile, basis_home, numerics)
         _capi.check(_capi.lib().dz_batch_create(template.handle, self.B, C.byref(o),
                                                 C.byref(self._h)))
 
@@ -239,7 +242,7 @@ def solve_batch_multi(template: Template, theta: np.ndarray, n_gpus: int = 0, *,
         a = getattr(res, name)
         setattr(r, name, None if a is None else a.ctypes.data)
     o = _options(0, max_pivots, trace_cap, kw.get("worker_warps", 0), kw.get("ctas_per_sm", 0), None, False,
-                 kw.get("basis_home", 0))
+                 kw.get("basis_home", 0), kw.get("numerics", "exact"))
     _capi.check(_capi.lib().dz_solve_batch_multi(t.handle, B, _vp(theta), int(n_gpus), C.byref(o), C.byref(r)))
     res.values = res.values[:, : t.n_orig]
     return res

@@ -120,6 +120,7 @@ int dz_template_get_arrays(const dz_template *t, int64_t *col_ptr, int32_t *row_
 int dz_template_pack_theta(const dz_template *t, const dz_model *model, double *theta);
 
 /* ---- solve options ---------------------------------------------------------- */
+enum { DZ_NUMERICS_EXACT = 0, DZ_NUMERICS_FAST = 1 };
 typedef struct dz_options {
     int32_t device;       /* CUDA device ordinal                                       */
     int64_t max_pivots;   /* <=0: default watchdog 100*(m+n_int)+1000                  */
@@ -136,6 +137,14 @@ typedef struct dz_options {
                              per-LP vectors in HBM (chosen automatically when they
                              exceed shared memory: m in the thousands), 4 = the on-chip
                              coupled-core kernel (the automatic choice for m_int <= 256) */
+    int32_t numerics;     /* DZ_NUMERICS_EXACT (0, the default): the reference's floating-point
+                             operations in the reference's order -- bit-identical pivot
+                             sequences.  DZ_NUMERICS_FAST (1): OPT-IN, never a default: one
+                             factorisation per pivot reused for BTRAN (the reference factorises
+                             B and B^T separately, simplex.rs:226-236), fused multiply-add,
+                             identity blocks of the basis eliminated symbolically.  Same pivot
+                             rules; results agree to rounding, not to the bit.  m_int <= 512
+                             (the batched classes and config 1); larger LPs: exact path only */
 } dz_options;
 void dz_options_default(dz_options *o);
 

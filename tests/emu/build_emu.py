@@ -20,7 +20,7 @@ def build(name: str = "", flags=(), force: bool = False) -> str:
     out_dir = os.path.join(HERE, "_build")
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, "libdantzig_b200_emu%s.so" % ("_" + name if name else ""))
-    srcs = [os.path.join(CSRC, f) for f in ("dz_kernel.cu", "dz_core.cu", "dz_grid.cu", "dz_capi.cu", "dz_lower.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("dz_kernel.cu", "dz_core.cu", "dz_grid.cu", "dz_fast.cu", "dz_capi.cu", "dz_lower.cpp")]
     srcs.append(os.path.join(HERE, "simt_emu.cpp"))
     deps = srcs + [os.path.join(HERE, "simt_emu.h"), os.path.join(CSRC, "dz_internal.h"), os.path.join(CSRC, "dz_device.cuh"),
                    os.path.join(ROOT, "include", "dantzig_b200.h")]

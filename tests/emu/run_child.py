@@ -4,6 +4,7 @@ results against the golden fixtures / the oracle.
 
     run_child.py golden <shapes: e.g. "-1:0,0:0,1:2"> <workload:count> ...
     run_child.py kats
+    run_child.py fast <workload:count> ...
 """
 import hashlib
 import json
@@ -45,6 +46,34 @@ def golden(shapes, specs):
     return out
 
 
+def fast(specs):
+    """Opt-in fast numerics (dz_fast.cu) against the golden fixtures: NOT bit parity -- status equal,
+    objective within 1e-9 relative, primal values within 1e-7, and (on these well-posed workloads)
+    the same pivot count."""
+    out = {}
+    for spec in specs:
+        wl, n = spec.split(":")
+        w = cases.GOLDEN_WORKLOADS[wl]()
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", wl + ".json")))
+        n = min(int(n), w.B)
+        t = Template(w.structure)
+        res = solve_batch(t, w.theta[:n], numerics="fast")
+        again = solve_batch(t, w.theta[:n], numerics="fast")
+        exact = solve_batch(t, w.theta[:n])
+        bad = 0
+        for i in range(n):
+            e = g["lps"][i]
+            gold_obj = struct.unpack("<d", bytes.fromhex(e["objective_bits"]))[0]
+            ok = res.status[i] == e["status"] and res.pivots[i] == e["pivots"]
+            if e["status"] == 0:
+                ok = ok and abs(res.objective[i] - gold_obj) <= 1e-9 * max(1.0, abs(gold_obj)) \
+                    and np.abs(res.values[i] - exact.values[i]).max() <= 1e-7
+            ok = ok and bits(res.objective[i]) == bits(again.objective[i]) and res.trace_hash[i] == again.trace_hash[i]
+            bad += (not ok)
+        out["fast:" + wl] = [bad, n]
+    return out
+
+
 def kats():
     from oracle import dzo_py
 
@@ -73,7 +102,9 @@ def kats():
 
 if __name__ == "__main__":
     assert "emulator" in device_info(0)["name"].lower(), "run_child.py must run on an emulator build"
-    if sys.argv[1] == "golden":
+    if sys.argv[1] == "fast":
+        print("EMU " + json.dumps(fast(sys.argv[2:])))
+    elif sys.argv[1] == "golden":
         shapes = [tuple(int(x) for x in s.split(":")) for s in sys.argv[2].split(",")]
         print("EMU " + json.dumps(golden(shapes, sys.argv[3:])))
     else:
