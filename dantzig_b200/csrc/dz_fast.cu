@@ -11,6 +11,13 @@
 //     (:231-236); the reference factorises B and an explicit B^T separately.
 //   * Fused multiply-add everywhere; reciprocal-multiply instead of division in the
 //     elimination.
+//   * Tolerance-guarded tests where the reference has none: the ratio test ignores direction
+//     components below 1e-9 and treats a negative perturbed value as zero (the reference
+//     tests `ratio > 0.0` only, simplex.rs:455), and optimality is accepted at mu* <= 1e-9
+//     (the reference: 1e-12, :283).  On well-posed LPs the pivots are the reference's; on
+//     the LPs where the reference's arithmetic ends in a false "infeasible"/"unbounded" or
+//     in the safe_divide panic (about half of config 1's instances) this path still ends at
+//     the optimum (checked against HiGHS in tests/test_fast_mode.py).
 //   * The factorisation is restricted to the part of the basis that is not an identity
 //     block.  With the basis columns split into slacks (unit columns) and structurals,
 //     and the rows into S (slack basic) and R (slack nonbasic),
@@ -49,6 +56,8 @@ namespace dz {
 namespace {
 
 enum { FC_LP = 0, FC_WORDS = 8 };
+constexpr double kFastPivTol = 1e-9; // ratio tests of the fast path ignore |direction| below this
+constexpr double kFastOptTol = 1e-9; // ... and its optimality test accepts a parameter mu* up to this
 
 // Slots of the optional per-LP cycle profile (BatchDev::prof, 16 per LP).
 enum { FP_STATUS = 0, FP_LISTS, FP_BUILD, FP_GJ, FP_FTRAN, FP_BTRAN, FP_PRICE, FP_RATIO, FP_UPDATE,
@@ -141,11 +150,19 @@ __device__ __forceinline__ int fast_find_second(Fast &c, double mu, const double
     cd.key[0] = 0.0;
     cd.idx[0] = -1;
     for (int k = c.tid; k < len; k += c.NT) {
-        const double denom = fma(mu, yb[k], y[k]);
-        const double ratio = dy[k] / denom;
-        if (ratio > 0.0 && beats(ratio, k, cd.key[0], cd.idx[0])) {
-            cd.key[0] = ratio;
-            cd.idx[0] = k;
+        // tolerance-guarded (the reference tests ratio > 0.0 and nothing else, simplex.rs:455): the
+        // perturbed value y + mu * ybar is nonnegative by the method's invariant, so a negative one is
+        // rounding noise and counts as zero, and a direction component within kFastPivTol of zero does
+        // not block the step.  On well-posed LPs this selects the reference's index.
+        const double d = dy[k];
+        if (d > kFastPivTol) {
+            double denom = fma(mu, yb[k], y[k]);
+            if (denom < 0.0) denom = 0.0;
+            const double ratio = d / denom; // +inf on a degenerate step: first index wins
+            if (beats(ratio, k, cd.key[0], cd.idx[0])) {
+                cd.key[0] = ratio;
+                cd.idx[0] = k;
+            }
         }
     }
     block_argmax<1>(cd, c.red_key, c.red_idx, c.parity, c.NW, c.tid, false);
@@ -219,7 +236,7 @@ __device__ __forceinline__ void gj_candidate(Fast &c, int j, int skip) {
 }
 
 // Generic in-place Gauss-Jordan inversion of K where it lies (shared memory or the HBM workspace):
-// any k, one CTA barrier per step (the pivot search of column j+1 is folded into the update of
+// any k, two CTA barriers per step (the pivot search of column j+1 is folded into the update of
 // step j).  The fallback for k beyond the register-tiled classes below.
 __device__ __forceinline__ bool gj_generic(Fast &c) {
     const int k = c.k, S = c.S, tid = c.tid, lane = c.lane, warp = c.warp, NW = c.NW;
@@ -250,6 +267,7 @@ __device__ __forceinline__ bool gj_generic(Fast &c) {
             break;
         }
         const double r = 1.0 / K[ip * S + j];
+        __syncthreads(); // everyone has the pivot before the pivot row's owner overwrites it below
         if (tid == 0) {
             c.pr[j] = ip;
             c.prinv[ip] = j;
@@ -700,7 +718,9 @@ dz_fast_kernel(const TemplateDev T, const BatchDev Bt, const int capK) {
             if (q0 >= 0 && p0 >= 0) {
                 const double primal = -c.x[p0] / c.xb[p0];
                 const double dual = -c.z[q0] / c.zb[q0];
-                if (primal <= 1e-12 && dual <= 1e-12) break;
+                // (the reference stops at 1e-12, simplex.rs:283; rounding residue at m_int in the hundreds is
+                // larger than that and sends it into one more, ill-posed pivot: the false "infeasible")
+                if (primal <= kFastOptTol && dual <= kFastOptTol) break;
                 if (primal < dual) {
                     primal_step = true;
                     mu = dual;

@@ -177,6 +177,9 @@ def test_fast_against_highs_where_the_reference_breaks_down(wl):
 def test_fast_through_the_rust_module():
     """rust.solve_batch(..., numerics="fast") -- the batched front door of the drop-in module."""
     import dantzig_b200.rust as rs
+    from tests.test_gpu_parity import _frontend
+
+    _frontend(rs)                                       # dantzig.exceptions for the module's error mapping
 
     def lp(k):
         x, y = rs.Variable(lb=0.0, ub=None), rs.Variable(lb=0.0, ub=None)
