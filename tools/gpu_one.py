@@ -1,6 +1,6 @@
 """One launch of a chosen kernel on a chosen workload (ncu target).
 
-    gpu_one.py c2|c5 <B> [worker_warps] [basis_home] [ctas_per_sm]     batched kernels
+    gpu_one.py c2|c5 <B> [worker_warps] [basis_home] [ctas_per_sm] [fast]   batched kernels
     gpu_one.py c3|c4 <prefix>                                          whole-GPU single-LP kernel
 """
 import sys, os
@@ -21,7 +21,8 @@ else:
     ww = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     home = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     cps = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    numerics = "fast" if len(sys.argv) > 6 and sys.argv[6] == "fast" else "exact"
     w = generate.config2(n) if which == "c2" else generate.config5(n)
-    b = Batch(Template(w.structure), w.B, worker_warps=ww, basis_home=home, ctas_per_sm=cps)
+    b = Batch(Template(w.structure), w.B, worker_warps=ww, basis_home=home, ctas_per_sm=cps, numerics=numerics)
     b.upload(w.theta); b.solve(); r = b.download(light=True)
     print(which, "B", n, b.launch_info(), "ms %.2f" % b.kernel_ms(), "optimal", int((r.status == 0).sum()), "pivots", int(r.pivots.sum()))

@@ -19,6 +19,8 @@ caps = []
 for name, tag, kernel in (("warp_c5", "c5", "dz_batch_kernel<1,true,8,6> (warp per LP, config-5 LPs)"),
                           ("warp_c2", "c2", "dz_batch_kernel<1,true,4,3> (warp per LP, config-2 LPs)"),
                           ("core_c5", "c5-core", "dz_core_kernel<6,256> (coupled core on chip, 2 CTAs/SM)"),
+                          ("fast_c2", "c2_fast", "dz_fast_kernel<128> (opt-in fast numerics, config-2 LPs)"),
+                          ("fast_c5", "c5_fast", "dz_fast_kernel<512> (opt-in fast numerics, config-5 LPs)"),
                           ("grid_c4", "c4", "dz_grid_kernel (config 4, 60-pivot prefix)"),
                           ("grid_c3", "c3", "dz_grid_kernel (config 3, 60-pivot prefix)")):
     try:
