@@ -83,6 +83,16 @@ def _lib_sha16() -> str:
     return hashlib.sha256(open(_capi.LIB_PATH, "rb").read()).hexdigest()[:16]
 
 
+def _src_sha16() -> str:
+    """Hash of the kernel SOURCES (dantzig_b200/csrc + the public header): what identifies a build
+    across machines -- two nvcc builds of the same sources are not byte-identical."""
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "dantzig_b200", "csrc")
+    for f in sorted(os.listdir(csrc)) + [os.path.join("..", "..", "include", "dantzig_b200.h")]:
+        h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 # --------------------------------------------------------------------------- workloads
 def batched_workload(name: str, count: int, first: int):
     from dantzig_b200 import generate
@@ -247,12 +257,14 @@ def measured_peaks() -> dict:
 
 def recorded_traffic(tag: str, units: float, prefix: int | None = None):
     """DRAM bytes per launch from the committed ncu capture of this workload's kernel -- only if
-    that capture was taken on the very library that is loaded now (profiles/traffic.json holds
-    bytes per LP, or per launch of a pivot prefix, with the library hash)."""
+    that capture was taken on a build of the very sources that are loaded now (profiles/traffic.json
+    holds bytes per LP, or per launch of a pivot prefix, with the source hash and the hash of the
+    library binary the capture ran on)."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         for e in t.get("captures", []):
-            if e.get("lib_sha16") == _lib_sha16() and e.get("tag") == tag:
+            same = e.get("src_sha16") == _src_sha16() or e.get("lib_sha16") == _lib_sha16()
+            if same and e.get("tag") == tag:
                 if e.get("prefix") is not None:
                     return e["dram_bytes_per_unit"] if prefix == e["prefix"] else None
                 return e["dram_bytes_per_unit"] * units
@@ -461,7 +473,7 @@ def run_gpu(args) -> None:
                              f"contiguous LP-id ranges of the {total}-LP batch per rank; no data-path collective; "
                              "all_gather of status/objective/pivots inside the e2e region"),
                 "l2": f"256 MB flush before every timed step (inputs {theta.nbytes / 1e6:.0f} MB)",
-                "launch": info, "lib_sha16": _lib_sha16(),
+                "launch": info, "lib_sha16": _lib_sha16(), "src_sha16": _src_sha16(),
                 "status_hist": np.bincount(full["status"], minlength=5).tolist(),
                 "pivots_per_step_rank0": pivots_rank,
             },

@@ -1,10 +1,14 @@
 """profiles/traffic.json from the ncu captures of tools/gpu_final_evidence.sh (gpurun_out/final/):
-DRAM bytes per unit (LP, or launch of a pivot prefix) of each kernel, keyed by the library hash the
-captures were taken on.  bench.py reports roofline.traffic only when that hash is the loaded library's."""
+DRAM bytes per unit (LP, or launch of a pivot prefix) of each kernel, keyed by the hash of the kernel
+sources (and of the library binary) the captures were taken on.  bench.py reports roofline.traffic only
+when the loaded build comes from the same sources."""
 import csv, json, os, re, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "final")
 sha = open(os.path.join(src, "lib_sha16.txt")).read().strip()
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (the source hash; run this while the sources are the ones the captures were built from)
+src_sha = bench._src_sha16()
 def dram(name):
     rows = list(csv.reader(open(os.path.join(src, "ncu_%s_raw.csv" % name))))
     rows = [r for r in rows if len(r) > 10]
@@ -33,7 +37,7 @@ for name, tag, kernel in (("warp_c5", "c5", "dz_batch_kernel<1,true,8,6> (warp p
     n = int(m.group(1))
     total = d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"]
     single = name.startswith("grid")
-    caps.append({"tag": tag, "kernel": kernel, "lib_sha16": sha, "units_in_capture": n,
+    caps.append({"tag": tag, "kernel": kernel, "lib_sha16": sha, "src_sha16": src_sha, "units_in_capture": n,
                  "unit": "launch of a %d-pivot prefix" % n if single else "LP",
                  "dram_bytes_read": d["dram__bytes_read.sum"], "dram_bytes_write": d["dram__bytes_write.sum"],
                  "dram_bytes_per_unit": total if single else total / n,
