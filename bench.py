@@ -83,12 +83,23 @@ def _lib_sha16() -> str:
     return hashlib.sha256(open(_capi.LIB_PATH, "rb").read()).hexdigest()[:16]
 
 
-def _src_sha16() -> str:
-    """Hash of the kernel SOURCES (dantzig_b200/csrc + the public header): what identifies a build
-    across machines -- two nvcc builds of the same sources are not byte-identical."""
+KERNEL_FILES = {  # traffic.json tag -> the source file that defines its kernel
+    "c5": "dz_kernel.cu", "c2": "dz_kernel.cu", "c5-core": "dz_core.cu", "c3": "dz_grid.cu", "c4": "dz_grid.cu",
+    "c2_fast": "dz_fast.cu", "c5_fast": "dz_fast.cu", "c5_fast_dmma": "dz_fast.cu",
+}
+
+
+def _src_sha16(tag: str | None = None) -> str:
+    """Hash of kernel SOURCES: what identifies a build across machines (two nvcc builds of the same
+    sources are not byte-identical).  With a traffic.json tag: that kernel's file plus the shared
+    device headers; without: everything under dantzig_b200/csrc plus the public header."""
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "dantzig_b200", "csrc")
-    for f in sorted(os.listdir(csrc)) + [os.path.join("..", "..", "include", "dantzig_b200.h")]:
+    if tag is None:
+        files = sorted(os.listdir(csrc)) + [os.path.join("..", "..", "include", "dantzig_b200.h")]
+    else:
+        files = [KERNEL_FILES[tag], "dz_device.cuh", "dz_internal.h"]
+    for f in files:
         h.update(open(os.path.join(csrc, f), "rb").read())
     return h.hexdigest()[:16]
 
@@ -263,7 +274,7 @@ def recorded_traffic(tag: str, units: float, prefix: int | None = None):
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         for e in t.get("captures", []):
-            same = e.get("src_sha16") == _src_sha16() or e.get("lib_sha16") == _lib_sha16()
+            same = e.get("src_sha16") == _src_sha16(tag) or e.get("lib_sha16") == _lib_sha16()
             if same and e.get("tag") == tag:
                 if e.get("prefix") is not None:
                     return e["dram_bytes_per_unit"] if prefix == e["prefix"] else None

@@ -573,7 +573,11 @@ int dz_batch_solve(dz_batch *b) {
                                     (size_t)b->plan.teams, b->stream));
     int rc;
     if (b->plan.fast_mode) {
-        rc = dz::launch_fast(b->tview, b->bd, b->plan, b->stream, &g_err);
+        // worker_warps == 2: the blocked tensor-core (DMMA) elimination instead of the step-by-step
+        // one (A/B switch of the fast kernel; same pivots, rounding differs in the last bits)
+        dz::BatchDev fd = b->bd;
+        fd.resume = b->opt.worker_warps == 2 ? 1 : 0;
+        rc = dz::launch_fast(b->tview, fd, b->plan, b->stream, &g_err);
     } else if (b->plan.grid_mode) {
         DZ_CUDA(cudaMemsetAsync(b->grid.bar, 0, 4 * sizeof(unsigned), b->stream));
         rc = dz::launch_grid(b->tview, b->bd, b->grid, b->plan, b->stream, &g_err);

@@ -89,6 +89,7 @@ struct Fast {
     double *Kg;
     double *K;
     int k, S;
+    bool blocked; // blocked tensor-core elimination (opt-in A/B switch) instead of the step-by-step tiled loop
     unsigned long long n_lu, n_solve, n_price;
 };
 
@@ -310,6 +311,184 @@ __device__ __forceinline__ double fast_rcp(double x) {
 #endif
 }
 
+// D = A * B + C on the FP64 tensor cores: one m8n8k4 tile per warp.  Fragments (PTX ISA, mma.m8n8k4
+// .f64): with g = lane >> 2 and t = lane & 3, a = A[g][t], b = B[t][g], (c0, c1) = C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, const double a, const double b) {
+#ifdef DZ_EMU // test-only restatement of the fragment layout on the SIMT emulator
+    const int lane = (int)threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double d0 = c0, d1 = c1;
+    for (int kk = 0; kk < 4; ++kk) {
+        const double ak = __shfl_sync(kFull, a, g * 4 + kk);
+        const double b0 = __shfl_sync(kFull, b, (2 * t) * 4 + kk);
+        const double b1 = __shfl_sync(kFull, b, (2 * t + 1) * 4 + kk);
+        d0 = fma(ak, b0, d0);
+        d1 = fma(ak, b1, d1);
+    }
+    c0 = d0;
+    c1 = d1;
+#else
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+#endif
+}
+
+// BLOCKED in-place Gauss-Jordan inversion of K in shared memory (k <= 16 * CB), four elimination
+// steps per pass over the matrix.  Within a panel of four columns every step is carried out on
+// the panel's columns only: warp 0 searches the step's column (REDUX on the magnitude bits,
+// smallest row on ties) and publishes the pivot row and the reciprocal of the pivot; then the
+// threads form the multipliers (G, k x 4, stored negated), update the panel's four columns in
+// place, and record the pivot row as it stands at that step outside the panel (U, 4 x columns,
+// zero on the panel's columns).  After the four steps every warp applies the rank-4 update
+// K += (-G) U to the whole matrix as 8 x 8 tiles on the FP64 TENSOR CORES (mma.m8n8k4.f64: the
+// panel width is the instruction's k).  The k x k update runs once per four steps.  Same pivots as
+// the step-by-step loop.  MEASURED (profiles/r02_fast_mode.md): no faster than the step-by-step
+// loop at k ~ 34 / 68 (config 2: 24.9 against 26.0 kLP/s, config 5: 1.47 against 1.51 kLP/s) -- a step
+// is a chain of short dependent phases (search ~900 cycles, panel update ~900, a quarter of the
+// tile pass ~1000 at config 5), not the k x k traffic -- so it is an opt-in switch
+// (dz_options.worker_warps == 2 together with DZ_NUMERICS_FAST), not the default.
+template <int CB>
+__device__ __forceinline__ void gj_blocked(double *K, const int k, const int tid, const int NT, double *Gbuf,
+                                           double *Ubuf, double *colj, double *pub, int *pr, int *prinv,
+                                           double *rinv, int *okflag, long long *prof) {
+    long long tq = (prof && tid == 0) ? clock64() : 0;
+    constexpr int S = 16 * CB + 1;
+    const int lane = tid & 31, warp = tid >> 5, NW = NT >> 5;
+    const int ncol = ((k + 15) >> 4) << 4; // columns in use, padded (the padding columns are zero)
+    unsigned long long pd0 = 0ull, pd1 = 0ull; // warp 0: rows already used as pivot rows
+    bool ok = true;                            // warp 0
+    for (int j0 = 0; j0 < k; j0 += 4) {
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s) {
+            const int col = j0 + s;
+            if (warp == 0) {
+                int p = -1;
+                double r = 0.0;
+                if (col < k && ok) {
+                    double kb = 0.0;
+                    int ib = 0x7fffffff;
+#pragma unroll
+                    for (int q = 0; q < (CB + 1) / 2; ++q) {
+                        const int i = lane + 32 * q;
+                        if (i < k) {
+                            const double v0 = K[i * S + col];
+                            colj[i] = v0;
+                            const bool done = q < 2 ? ((pd0 >> (i & 63)) & 1ull) : ((pd1 >> (i & 63)) & 1ull);
+                            double av = fabs(v0);
+                            if (!(av == av)) av = 1.7976931348623157e308;
+                            if (!done && av > kb) {
+                                kb = av;
+                                ib = i;
+                            }
+                        }
+                    }
+                    const unsigned hi = (unsigned)__double2hiint(kb), lo = (unsigned)__double2loint(kb);
+                    const unsigned mh = __reduce_max_sync(kFull, hi);
+                    const unsigned ml = __reduce_max_sync(kFull, hi == mh ? lo : 0u);
+                    p = __reduce_min_sync(kFull, (hi == mh && lo == ml) ? ib : 0x7fffffff);
+                    if ((mh | ml) == 0u || mh >= 0x7e000000u || p >= k) { // zero, huge or non-finite pivot
+                        ok = false;
+                        p = -1;
+                    } else {
+                        __syncwarp();
+                        r = fast_rcp(colj[p]);
+                        if (p < 64) pd0 |= 1ull << p; else pd1 |= 1ull << (p - 64);
+                    }
+                }
+                if (lane == 0) {
+                    pub[0] = r;
+                    reinterpret_cast<int *>(pub + 1)[0] = p;
+                    if (p >= 0) {
+                        pr[col] = p;
+                        prinv[p] = col;
+                        rinv[col] = r;
+                    }
+                }
+            }
+            if (prof && tid == 0) {
+                const long long t_ = clock64();
+                prof[11] += t_ - tq;
+                tq = t_;
+            }
+            __syncthreads();
+            if (prof && tid == 0) {
+                const long long t_ = clock64();
+                prof[12] += t_ - tq;
+                tq = t_;
+            }
+            {
+                const double r = pub[0];
+                const int p = reinterpret_cast<const int *>(pub + 1)[0];
+                if (p >= 0) {
+                    // the pivot row as it stands at this step, outside the panel's columns: the rows of
+                    // the earlier steps of this panel have not been applied to it yet
+                    for (int c = tid; c < ncol; c += NT) {
+                        double u = 0.0;
+                        if (c < j0 || c >= j0 + 4) {
+                            u = K[p * S + c];
+                            for (int t = 0; t < s; ++t) u = fma(Gbuf[p * 4 + t], Ubuf[t * ncol + c], u);
+                        }
+                        Ubuf[s * ncol + c] = u;
+                    }
+                    // multipliers; the panel's columns in place (column `col` becomes the identity
+                    // column of the pivot row, with the multipliers negated)
+                    for (int i = tid; i < k; i += NT) {
+                        if (i == p) {
+                            Gbuf[i * 4 + s] = 0.0;
+                            K[i * S + col] = 1.0;
+                        } else {
+                            const double g = colj[i] * r;
+                            Gbuf[i * 4 + s] = -g;
+                            K[i * S + col] = -g;
+                            if (g != 0.0) {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t)
+                                    if (t != s && j0 + t < k) K[i * S + j0 + t] = fma(-g, K[p * S + j0 + t], K[i * S + j0 + t]);
+                            }
+                        }
+                    }
+                } else { // past the last column, or after a breakdown: a step that changes nothing
+                    for (int c = tid; c < ncol; c += NT) Ubuf[s * ncol + c] = 0.0;
+                    for (int i = tid; i < k; i += NT) Gbuf[i * 4 + s] = 0.0;
+                }
+            }
+            __syncthreads();
+            if (prof && tid == 0) {
+                const long long t_ = clock64();
+                prof[14] += t_ - tq;
+                tq = t_;
+            }
+        }
+        {
+            const int nct = ncol >> 3, nrt = (k + 7) >> 3;
+            const int g = lane >> 2, t = lane & 3;
+            for (int tile = warp; tile < nrt * nct; tile += NW) {
+                const int rt = tile / nct, ct = tile - rt * nct;
+                const int row = 8 * rt + g, c = 8 * ct + 2 * t;
+                const double a = row < k ? Gbuf[row * 4 + t] : 0.0;
+                const double b = Ubuf[t * ncol + 8 * ct + g];
+                double c0 = 0.0, c1 = 0.0;
+                if (row < k) {
+                    c0 = K[row * S + c];
+                    c1 = K[row * S + c + 1];
+                }
+                dmma_m8n8k4(c0, c1, a, b);
+                if (row < k) {
+                    K[row * S + c] = c0;
+                    K[row * S + c + 1] = c1;
+                }
+            }
+        }
+        __syncthreads();
+        if (prof && tid == 0) {
+            const long long t_ = clock64();
+            prof[15] += t_ - tq;
+            tq = t_;
+        }
+    }
+    if (tid == 0) *okflag = ok ? 1 : 0;
+}
+
 // Tiled in-place Gauss-Jordan inversion of K in shared memory, for k <= 16 * CB.  The first
 // TY * 16 threads work: thread (ty, tx) updates rows ty, ty + TY, ... and the CB columns
 // tx + 16 * b, the pivot row's entries held in registers for the whole step (K is stored with
@@ -467,7 +646,18 @@ __device__ __forceinline__ bool fast_factor(Fast &c, const TemplateDev &T, const
     } else {
         // (c.Ks, not K: the compiler then knows the address space and emits LDS/STS instead of
         // generic loads and stores)
-        if (use_cls == 1) {
+        // blocked (tensor-core) elimination, when asked for and its scratch fits the solve vectors that are idle
+        // during the factorisation: G (k x 4) in acc [NW x M], U (4 x padded columns) in dxv..tK [4 x M]
+        const bool blocked = c.blocked && 4 * (((k + 15) >> 4) << 4) <= 4 * c.M;
+        if (blocked) {
+            if (use_cls == 1) {
+                gj_blocked<2>(c.Ks, k, tid, c.NT, c.acc, c.dxv, c.uK, c.red_key, c.pr, c.prinv, c.rinv, &c.ctl[1], c.prof);
+            } else if (use_cls == 2) {
+                gj_blocked<4>(c.Ks, k, tid, c.NT, c.acc, c.dxv, c.uK, c.red_key, c.pr, c.prinv, c.rinv, &c.ctl[1], c.prof);
+            } else if (NTH >= 512) {
+                gj_blocked<8>(c.Ks, k, tid, c.NT, c.acc, c.dxv, c.uK, c.red_key, c.pr, c.prinv, c.rinv, &c.ctl[1], c.prof);
+            }
+        } else if (use_cls == 1) {
             gj_tiled<NTH / 16, 2>(c.Ks, k, tid, c.bK, c.uK, c.pr, c.prinv, c.rinv, &c.ctl[1], c.prof);
         } else if (use_cls == 2) {
             gj_tiled<NTH / 16, 4>(c.Ks, k, tid, c.bK, c.uK, c.pr, c.prinv, c.rinv, &c.ctl[1], c.prof);
@@ -626,6 +816,7 @@ dz_fast_kernel(const TemplateDev T, const BatchDev Bt, const int capK) {
     c.lane = c.tid & 31;
     c.warp = c.tid >> 5;
     c.parity = 0;
+    c.blocked = Bt.resume == 1; // BatchDev::resume is unused by this kernel otherwise: 1 = blocked tensor-core elimination
     const int M = c.M, Nn = c.Nn, tid = c.tid;
     {
         double *dp = reinterpret_cast<double *>(smem_raw);

@@ -127,7 +127,10 @@ typedef struct dz_options {
     int32_t trace_cap;    /* per-LP pivot trace entries to record (0 = none)           */
     int32_t worker_warps; /* 0 = auto; >0 = CTA per LP with that many worker warps;
                              -1 = one warp per LP (no CTA barriers).  Tuning knob,
-                             never changes results                                    */
+                             never changes results of the exact path.  With
+                             DZ_NUMERICS_FAST: 2 = blocked elimination with the rank-4
+                             update on the FP64 tensor cores (same pivots; rounding
+                             differs in the last bits), anything else = step by step  */
     int32_t ctas_per_sm;  /* 0 = auto                                                  */
     void *stream;         /* cudaStream_t to launch on (NULL = the library's stream)   */
     int32_t profile;      /* 1 = record per-LP phase cycle counts (dz_batch_result.prof) */

@@ -60,6 +60,7 @@ def fast(specs):
         res = solve_batch(t, w.theta[:n], numerics="fast")
         again = solve_batch(t, w.theta[:n], numerics="fast")
         exact = solve_batch(t, w.theta[:n])
+        dmma = solve_batch(t, w.theta[:n], numerics="fast", worker_warps=2)   # blocked tensor-core elimination
         bad = 0
         for i in range(n):
             e = g["lps"][i]
@@ -69,6 +70,8 @@ def fast(specs):
                 ok = ok and abs(res.objective[i] - gold_obj) <= 1e-9 * max(1.0, abs(gold_obj)) \
                     and np.abs(res.values[i] - exact.values[i]).max() <= 1e-7
             ok = ok and bits(res.objective[i]) == bits(again.objective[i]) and res.trace_hash[i] == again.trace_hash[i]
+            ok = ok and dmma.status[i] == res.status[i] and dmma.pivots[i] == res.pivots[i] and \
+                abs(dmma.objective[i] - res.objective[i]) <= 1e-9 * max(1.0, abs(res.objective[i]))
             bad += (not ok)
         out["fast:" + wl] = [bad, n]
     return out

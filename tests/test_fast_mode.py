@@ -36,7 +36,9 @@ def _emu_lib():
 
 def test_fast_numerics_on_the_emulator():
     """Every size class of the tiled Gauss-Jordan inversion (k <= 32, <= 64 on 128 threads; <= 128
-    on 512 threads) and the generic fallback (small_40x80: k up to 80 on a 128-thread CTA)."""
+    on 512 threads), the generic fallback (small_40x80: k up to 80 on a 128-thread CTA), and the
+    blocked tensor-core variant of each class (the emulator restates mma.m8n8k4.f64's fragment
+    layout; the GPU test checks the real instruction)."""
     env = dict(os.environ, DZ_LIB=_emu_lib(), DZ_LIB_TEST_ONLY="1")
     r = subprocess.run([sys.executable, os.path.join(EMU, "run_child.py"), "fast", "tiny_4x6:8", "small_8x16:6",
                         "mixed_9x12:6", "mixed_20x40:3", "packing_24x48:2", "c2_32x64:2", "small_40x80:1",
@@ -127,6 +129,23 @@ def test_fast_on_baseline_batches(wl, count):
     opt, rel, dv = _agree(ex, fa)
     assert rel <= REL_OBJ and dv <= ABS_VAL
     assert (fa.pivots[opt] != ex.pivots[opt]).mean() <= 0.05
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wl,count", [("c2", 512), ("c5", 74)])
+def test_fast_blocked_tensor_core_elimination(wl, count):
+    """worker_warps=2 with numerics="fast": four elimination steps per pass, the rank-4 update on the
+    FP64 tensor cores (mma.m8n8k4.f64).  Same pivots as the step-by-step loop, results to rounding."""
+    from dantzig_b200 import Template, generate, solve_batch
+
+    w = generate.config2(count) if wl == "c2" else generate.config5(count)
+    t = Template(w.structure)
+    fa = solve_batch(t, w.theta, numerics="fast")
+    bl = solve_batch(t, w.theta, numerics="fast", worker_warps=2)
+    assert (bl.status == fa.status).all() and (fa.status == 0).all()
+    assert (bl.pivots == fa.pivots).mean() >= 0.98
+    rel = np.abs(bl.objective - fa.objective) / np.maximum(1.0, np.abs(fa.objective))
+    assert rel.max() <= REL_OBJ and np.abs(bl.values - fa.values).max() <= ABS_VAL
 
 
 @pytest.mark.gpu

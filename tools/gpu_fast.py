@@ -50,9 +50,10 @@ tput("c2-prof", generate.config2(592), profile=True)
 if "--prof-only" in sys.argv:
     tput("c5-prof", generate.config5(148), profile=True)
     sys.exit(0)
-for cps in (3, 4):
-    tput("c2", w2, ctas_per_sm=cps)
+tput("c2", w2)
+tput("c2-blocked-dmma", w2, worker_warps=2)
 w5 = generate.config5(2368)
 tput("c5-prof", generate.config5(296), profile=True)
 tput("c5", w5)
+tput("c5-blocked-dmma", w5, worker_warps=2)
 tput("c5-1184", generate.config5(1184))

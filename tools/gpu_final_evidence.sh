@@ -25,6 +25,7 @@ cap warp_c2 dz_batch_kernel "$SECS" c2 2048 -1
 cap core_c5 dz_core_kernel "$SECS" c5 296 0 4 2
 cap fast_c2 dz_fast_kernel "--set full --import-source on" c2 592 0 0 0 fast
 cap fast_c5 dz_fast_kernel "--set full --import-source on" c5 148 0 0 0 fast
+cap fast_c5_dmma dz_fast_kernel "--set full --import-source on" c5 148 2 0 0 fast
 cap grid_c4 dz_grid_kernel "--set full --import-source on" c4 60
 cap grid_c3 dz_grid_kernel "--set full --import-source on" c3 60
 tail -2 $O/smoke.log 2>/dev/null | tail -4; ls $O | wc -l

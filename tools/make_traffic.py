@@ -5,10 +5,16 @@ when the loaded build comes from the same sources."""
 import csv, json, os, re, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "final")
+only = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None   # capture names to refresh; others are kept
+old = {}
+try:
+    for e in json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["captures"]:
+        old[e["tag"]] = e
+except Exception:
+    pass
 sha = open(os.path.join(src, "lib_sha16.txt")).read().strip()
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402  (the source hash; run this while the sources are the ones the captures were built from)
-src_sha = bench._src_sha16()
 def dram(name):
     rows = list(csv.reader(open(os.path.join(src, "ncu_%s_raw.csv" % name))))
     rows = [r for r in rows if len(r) > 10]
@@ -25,8 +31,13 @@ for name, tag, kernel in (("warp_c5", "c5", "dz_batch_kernel<1,true,8,6> (warp p
                           ("core_c5", "c5-core", "dz_core_kernel<6,256> (coupled core on chip, 2 CTAs/SM)"),
                           ("fast_c2", "c2_fast", "dz_fast_kernel<128> (opt-in fast numerics, config-2 LPs)"),
                           ("fast_c5", "c5_fast", "dz_fast_kernel<512> (opt-in fast numerics, config-5 LPs)"),
+                          ("fast_c5_dmma", "c5_fast_dmma", "dz_fast_kernel<512>, blocked elimination on the FP64 tensor cores (worker_warps=2)"),
                           ("grid_c4", "c4", "dz_grid_kernel (config 4, 60-pivot prefix)"),
                           ("grid_c3", "c3", "dz_grid_kernel (config 3, 60-pivot prefix)")):
+    if only is not None and name not in only:
+        if tag in old:
+            caps.append(old[tag])
+        continue
     try:
         d = dram(name)
         log = open(os.path.join(src, "one_%s.log" % name)).read()
@@ -37,7 +48,7 @@ for name, tag, kernel in (("warp_c5", "c5", "dz_batch_kernel<1,true,8,6> (warp p
     n = int(m.group(1))
     total = d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"]
     single = name.startswith("grid")
-    caps.append({"tag": tag, "kernel": kernel, "lib_sha16": sha, "src_sha16": src_sha, "units_in_capture": n,
+    caps.append({"tag": tag, "kernel": kernel, "lib_sha16": sha, "src_sha16": bench._src_sha16(tag), "units_in_capture": n,
                  "unit": "launch of a %d-pivot prefix" % n if single else "LP",
                  "dram_bytes_read": d["dram__bytes_read.sum"], "dram_bytes_write": d["dram__bytes_write.sum"],
                  "dram_bytes_per_unit": total if single else total / n,
