@@ -274,10 +274,11 @@ class Solution:
         return _capi.STATUS_NAMES[self.status]
 
 
-def solve_model(model: ModelArrays, *, device: int = 0, max_pivots: int = 0) -> Solution:
-    """Replacement for ``Simplex::new(objective, constraints).solve()``."""
+def solve_model(model: ModelArrays, *, device: int = 0, max_pivots: int = 0, numerics: str = "exact") -> Solution:
+    """Replacement for ``Simplex::new(objective, constraints).solve()``.  ``numerics="fast"`` opts this one
+    solve into the fast-numerics kernel (lowered LPs of up to 512 rows; never the default)."""
     cm = model.as_c()
-    o = _options(device, max_pivots)
+    o = _options(device, max_pivots, numerics=numerics)
     sol = _capi.Solution()
     values = np.zeros(max(model.n_vars, 1), np.float64)
     _capi.check(_capi.lib().dz_solve_model(C.byref(cm), C.byref(o), C.byref(sol), _vp(values)))

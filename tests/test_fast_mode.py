@@ -193,6 +193,23 @@ def test_fast_against_highs_where_the_reference_breaks_down(wl):
 
 
 @pytest.mark.gpu
+def test_fast_single_lp_entry_on_config1():
+    """dz_solve_model with numerics = FAST: BASELINE configs[0] (100 x 200, mixed rows, free variables;
+    lowered 283 x 683).  The exact path reproduces the reference's outcome on these seeds (optimal,
+    safe_divide panic, false 'unbounded'); the fast path ends at the HiGHS optimum on all three."""
+    from dantzig_b200 import solve_model
+    from dantzig_b200.model import model_from_theta
+    from tests import cases
+
+    w = cases.GOLDEN_WORKLOADS["c1_100x200"]()
+    for i in range(w.B):
+        m = model_from_theta(w.structure, w.theta[i])
+        s = solve_model(m, numerics="fast")
+        best = _highs_max(m)
+        assert s.status == 0 and abs(s.objective - best) <= 1e-7 * max(1.0, abs(best)), (i, s.status, s.objective, best)
+
+
+@pytest.mark.gpu
 def test_fast_through_the_rust_module():
     """rust.solve_batch(..., numerics="fast") -- the batched front door of the drop-in module."""
     import dantzig_b200.rust as rs
