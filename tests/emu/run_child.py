@@ -48,8 +48,9 @@ def golden(shapes, specs):
 
 def fast(specs):
     """Opt-in fast numerics (dz_fast.cu) against the golden fixtures: NOT bit parity -- status equal,
-    objective within 1e-9 relative, primal values within 1e-7, and (on these well-posed workloads)
-    the same pivot count."""
+    objective within 1e-9 relative and (on these well-posed workloads) the same pivot count; two runs
+    bit-identical; the blocked tensor-core variant equal to 1e-9 with the same pivot count.  (Primal
+    values against the exact path are compared on the GPU, tests/test_fast_mode.py.)"""
     out = {}
     for spec in specs:
         wl, n = spec.split(":")
@@ -59,7 +60,6 @@ def fast(specs):
         t = Template(w.structure)
         res = solve_batch(t, w.theta[:n], numerics="fast")
         again = solve_batch(t, w.theta[:n], numerics="fast")
-        exact = solve_batch(t, w.theta[:n])
         dmma = solve_batch(t, w.theta[:n], numerics="fast", worker_warps=2)   # blocked tensor-core elimination
         bad = 0
         for i in range(n):
@@ -67,8 +67,7 @@ def fast(specs):
             gold_obj = struct.unpack("<d", bytes.fromhex(e["objective_bits"]))[0]
             ok = res.status[i] == e["status"] and res.pivots[i] == e["pivots"]
             if e["status"] == 0:
-                ok = ok and abs(res.objective[i] - gold_obj) <= 1e-9 * max(1.0, abs(gold_obj)) \
-                    and np.abs(res.values[i] - exact.values[i]).max() <= 1e-7
+                ok = ok and abs(res.objective[i] - gold_obj) <= 1e-9 * max(1.0, abs(gold_obj))
             ok = ok and bits(res.objective[i]) == bits(again.objective[i]) and res.trace_hash[i] == again.trace_hash[i]
             ok = ok and dmma.status[i] == res.status[i] and dmma.pivots[i] == res.pivots[i] and \
                 abs(dmma.objective[i] - res.objective[i]) <= 1e-9 * max(1.0, abs(res.objective[i]))
