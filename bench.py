@@ -91,14 +91,15 @@ KERNEL_FILES = {  # traffic.json tag -> the source file that defines its kernel
 
 def _src_sha16(tag: str | None = None) -> str:
     """Hash of kernel SOURCES: what identifies a build across machines (two nvcc builds of the same
-    sources are not byte-identical).  With a traffic.json tag: that kernel's file plus the shared
-    device headers; without: everything under dantzig_b200/csrc plus the public header."""
+    sources are not byte-identical).  With a traffic.json tag: the files that hold that kernel's
+    device code (its .cu and the shared device helpers); without: everything under dantzig_b200/csrc
+    plus the public header."""
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "dantzig_b200", "csrc")
     if tag is None:
         files = sorted(os.listdir(csrc)) + [os.path.join("..", "..", "include", "dantzig_b200.h")]
     else:
-        files = [KERNEL_FILES[tag], "dz_device.cuh", "dz_internal.h"]
+        files = [KERNEL_FILES[tag], "dz_device.cuh"]
     for f in files:
         h.update(open(os.path.join(csrc, f), "rb").read())
     return h.hexdigest()[:16]

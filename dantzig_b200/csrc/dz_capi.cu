@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #endif
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -86,6 +87,44 @@ static int template_on_device(dz_template *t, int device, dz::TemplateDev *view)
             }
     }
     const size_t o_rp = push(csr_ptr), o_rc = push(csr_col), o_rr = push(csr_ref);
+    // dense-rows structure (see TemplateDev): the longest common prefix of rows 0, 1, 2, ... over all
+    // structural columns whose references advance by one constant stride and keep their sign
+    int32_t dense_md = 0, dense_stride = 0;
+    std::vector<int32_t> dense_ref((size_t)h.n_int, -1);
+    {
+        int64_t md = -1;
+        int32_t stride = 0;
+        bool any = false;
+        for (int32_t col = 0; col < h.n_int && md != 0; ++col) {
+            if (h.slack_row[(size_t)col] >= 0) continue;
+            const int64_t e0 = h.col_ptr[(size_t)col], e1 = h.col_ptr[(size_t)col + 1];
+            if (e1 - e0 < 2 || h.val_ref[(size_t)e0] < 2 || h.val_ref[(size_t)e0 + 1] < 2) {
+                md = 0;
+                break;
+            }
+            const int32_t r0 = h.val_ref[(size_t)e0], st = (h.val_ref[(size_t)e0 + 1] >> 1) - (r0 >> 1);
+            if (!any) stride = st;
+            any = true;
+            if (st != stride || stride <= 0) {
+                md = 0;
+                break;
+            }
+            int64_t n = 0;
+            while (e0 + n < e1 && h.row_idx[(size_t)(e0 + n)] == (int32_t)n && h.val_ref[(size_t)(e0 + n)] >= 2 &&
+                   (h.val_ref[(size_t)(e0 + n)] & 1) == (r0 & 1) &&
+                   (h.val_ref[(size_t)(e0 + n)] >> 1) == (r0 >> 1) + (int32_t)n * stride)
+                ++n;
+            md = md < 0 ? n : std::min(md, n);
+            dense_ref[(size_t)col] = r0;
+        }
+        if (any && md >= 8) {
+            dense_md = (int32_t)md;
+            dense_stride = stride;
+        } else {
+            std::fill(dense_ref.begin(), dense_ref.end(), -1);
+        }
+    }
+    const size_t o_dr = push(dense_ref);
     DZ_CUDA(cudaSetDevice(device));
     dz_template::Dev d;
     d.device = device;
@@ -114,6 +153,9 @@ static int template_on_device(dz_template *t, int device, dz::TemplateDev *view)
     d.view.csr_ptr = d.blob + o_rp;
     d.view.csr_col = d.blob + o_rc;
     d.view.csr_ref = d.blob + o_rr;
+    d.view.dense_md = dense_md;
+    d.view.dense_stride = dense_stride;
+    d.view.dense_ref = d.blob + o_dr;
     t->devs.push_back(d);
     *view = d.view;
     return DZ_OK;

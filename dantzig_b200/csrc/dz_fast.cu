@@ -82,6 +82,7 @@ struct Fast {
     int *cmapK, *clistK; // basis position -> column of K / back
     int *pr, *prinv;    // elimination step -> its pivot row of K / back
     int *pdone;         // row of K already used as a pivot row
+    int *kref;          // [M] column of K -> signed theta reference of its row-0 entry (dense-rows templates)
     int *scan, *ctl;
     // the k x k working matrix
     double *Ks;
@@ -605,12 +606,29 @@ __device__ __forceinline__ void gj_tiled(double *K, const int k, const int tid, 
 // column, lanes on its entries.
 __device__ __forceinline__ void fast_gather(Fast &c, const TemplateDev &T, const double *__restrict__ theta, double *K) {
     const int k = c.k, S = c.S;
+    const int md = T.dense_md, st = T.dense_stride;
     for (int e = c.tid; e < k * S; e += c.NT) K[e] = 0.0;
+    if (md > 0)
+        for (int kc = c.tid; kc < k; kc += c.NT) c.kref[kc] = T.dense_ref[c.bas[c.clistK[kc]]];
     __syncthreads();
-    for (int kc = c.warp; kc < k; kc += c.NW) {
+    if (md > 0) {
+        // dense-rows template: rows 0 .. md-1 of every structural column sit at computed addresses of
+        // theta (A[r][j], row-major): one warp per row of R, lanes on the columns of K -- no loads of
+        // row_idx / val_ref, neighbouring lanes read neighbouring words
+        for (int r = c.warp; r < md; r += c.NW) {
+            const int kr = c.rmapK[r];
+            if (kr < 0) continue; // warp-uniform
+            for (int kc = c.lane; kc < k; kc += 32) {
+                const int ref = c.kref[kc];
+                const double a = __ldg(theta + (ref >> 1) + r * st);
+                K[kr * S + kc] = (ref & 1) ? -a : a;
+            }
+        }
+    }
+    for (int kc = c.warp; kc < k; kc += c.NW) { // (the rest of) every column through the template
         const int col = c.bas[c.clistK[kc]];
         const int e1 = T.col_ptr[col + 1];
-        for (int e = T.col_ptr[col] + c.lane; e < e1; e += 32) {
+        for (int e = T.col_ptr[col] + md + c.lane; e < e1; e += 32) {
             const int kr = c.rmapK[T.row_idx[e]];
             if (kr >= 0) K[kr * S + kc] = load_ref(theta, T.val_ref[e]);
         }
@@ -738,6 +756,24 @@ __device__ __forceinline__ void fast_ftran(Fast &c, const TemplateDev &T, const 
     // the column's entries) and adds a_rc * d_c for the rows of S into ITS OWN accumulator row,
     // so no two warps ever touch the same word; the NW partial sums of a row are then added in
     // warp order.  Deterministic, no floating-point atomics, no row-major copy of A needed.
+    const int md = T.dense_md, st = T.dense_stride;
+    if (md > 0) {
+        // dense-rows template: the rows of S among rows 0 .. md-1, one warp per row, lanes on the
+        // columns of K (computed addresses, fixed summation tree)
+        for (int r = c.warp; r < md; r += c.NW) {
+            const int ps = c.spos[r];
+            if (ps < 0) continue; // warp-uniform
+            double s = 0.0;
+            for (int kc = c.lane; kc < k; kc += 32) {
+                const int ref = c.kref[kc];
+                const double a = __ldg(theta + (ref >> 1) + r * st);
+                s = fma((ref & 1) ? -a : a, c.dxv[c.clistK[kc]], s);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
+            if (c.lane == 0) c.dxv[ps] -= s;
+        }
+    }
     {
         double *acc = c.acc + c.warp * M;
         for (int kc = c.warp; kc < k; kc += c.NW) {
@@ -746,7 +782,7 @@ __device__ __forceinline__ void fast_ftran(Fast &c, const TemplateDev &T, const 
             if (d == 0.0) continue; // warp-uniform
             const int col = c.bas[pc];
             const int e1 = T.col_ptr[col + 1];
-            for (int e = T.col_ptr[col] + c.lane; e < e1; e += 32) {
+            for (int e = T.col_ptr[col] + md + c.lane; e < e1; e += 32) {
                 const int r = T.row_idx[e];
                 if (c.rmapK[r] < 0) acc[r] = fma(load_ref(theta, T.val_ref[e]), d, acc[r]);
             }
@@ -851,6 +887,7 @@ dz_fast_kernel(const TemplateDev T, const BatchDev Bt, const int capK) {
         c.pr = ip, ip += M;
         c.prinv = ip, ip += M;
         c.pdone = ip, ip += M;
+        c.kref = ip, ip += M;
         c.nb = ip, ip += Nn;
         c.where = ip, ip += T.Nint;
         c.Kg = Bt.gws + (size_t)blockIdx.x * Bt.gws_stride;
@@ -968,6 +1005,24 @@ dz_fast_kernel(const TemplateDev T, const BatchDev Bt, const int capK) {
                                     const int e0 = T.col_ptr[col], e1 = T.col_ptr[col + 1];
                                     double s1 = 0.0;
                                     int e = e0 + sub;
+                                    if (T.dense_md > 0) {
+                                        // dense-rows template: rows 0 .. md-1 at computed addresses of theta
+                                        const int md = T.dense_md, st = T.dense_stride, ref = T.dense_ref[col];
+                                        const double *a = theta + (ref >> 1);
+                                        double s2 = 0.0, s3 = 0.0;
+                                        int r = sub;
+                                        for (; r + 12 < md; r += 16) {
+                                            s = fma(__ldg(a + r * st), c.vv[r], s);
+                                            s1 = fma(__ldg(a + (r + 4) * st), c.vv[r + 4], s1);
+                                            s2 = fma(__ldg(a + (r + 8) * st), c.vv[r + 8], s2);
+                                            s3 = fma(__ldg(a + (r + 12) * st), c.vv[r + 12], s3);
+                                        }
+                                        for (; r < md; r += 4) s = fma(__ldg(a + r * st), c.vv[r], s);
+                                        s = (s + s1) + (s2 + s3);
+                                        s = (ref & 1) ? s : -s; // dz = -a . v, and a odd reference is -theta
+                                        s1 = 0.0;
+                                        e += md;
+                                    }
                                     for (; e + 4 < e1; e += 8) {
                                         const double a0 = load_ref(theta, T.val_ref[e]);
                                         const double a1 = load_ref(theta, T.val_ref[e + 4]);
@@ -1125,7 +1180,7 @@ dz_fast_kernel(const TemplateDev T, const BatchDev Bt, const int capK) {
 
 size_t fast_fixed_smem_bytes(int M, int Nn, int Nint, int nwarps) {
     const size_t doubles = (8 + (size_t)nwarps) * (size_t)M + 3 * (size_t)Nn + 16 + 2 * 4 * kMaxWarps;
-    const size_t ints = 2 * 4 * kMaxWarps + 2 * kMaxWarps + FC_WORDS + 10 * (size_t)M + (size_t)Nn + (size_t)Nint;
+    const size_t ints = 2 * 4 * kMaxWarps + 2 * kMaxWarps + FC_WORDS + 11 * (size_t)M + (size_t)Nn + (size_t)Nint;
     return doubles * 8 + ints * 4 + 16;
 }
 

@@ -54,6 +54,13 @@ struct TemplateDev {
     const int32_t *csr_ptr;   // [M+1]
     const int32_t *csr_col;   // [nnz]
     const int32_t *csr_ref;   // [nnz]
+    // DENSE-ROWS structure (fast-numerics kernel): when every structural column starts with entries
+    // in rows 0 .. dense_md-1 whose theta references advance by the same stride from row to row
+    // (a dense user matrix A[r][j] stored row-major in theta, all rows of one sense), the kernel
+    // computes those addresses instead of loading row_idx / val_ref.  dense_ref[col] is the signed
+    // reference of the column's row-0 entry (-1 for slacks); dense_md == 0 switches it off.
+    int32_t dense_md, dense_stride;
+    const int32_t *dense_ref; // [Nint]
 };
 
 // Device view of one batch: inputs and outputs, all in HBM.
